@@ -1,0 +1,138 @@
+/* ofdis_b200.h -- C-ABI of the B200-native DIS optical-flow hot path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers
+ * and sizes, no C++/torch types.  Everything the reference's three classes do
+ * on the hot path is reachable from here:
+ *
+ *   reference interface (file:line)                       -> entry point
+ *   ------------------------------------------------------------------------
+ *   OFC::OFClass::OFClass            oflow.h:84-111,        ofdis_create + ofdis_upload_* +
+ *                                    oflow.cpp:32-363        ofdis_run + ofdis_get_flow
+ *   PatGridClass::InitializeGrid /   patchgrid.h:25-26,     ofdis_upload_level (binds I0,dI0,I1 of a level)
+ *     SetTargetImage                 patchgrid.cpp:98-132
+ *   PatGridClass::InitializeFromCoarserOF  patchgrid.cpp:195-211   ofdis_set_flow(level+1) / implicit in ofdis_run
+ *   PatGridClass::Optimize           patchgrid.cpp:134-141  ofdis_patgrid_optimize
+ *     (PatClass::InitializePatch, OptimizeIter  patch.cpp:57-88,119-212 -- fused into the same kernel)
+ *   PatGridClass::AggregateFlowDense patchgrid.cpp:213-397  ofdis_patgrid_aggregate
+ *   PatGridClass::GetQuePatchDis &c  patchgrid.h:42-44      ofdis_get_patches
+ *   VarRefClass::VarRefClass         refine_variational.h:37-39,    ofdis_varref_refine
+ *                                    refine_variational.cpp:25-116
+ *     (image_warp, get_derivatives, compute_smoothness, compute_data[_DE],
+ *      sub_laplacian, sor_coupled / sor_coupled_slow_but_readable_DE;
+ *      FDF1.0.1/opticalflow_aux.c:17-548, solver.c:77-466 -- device kernels)
+ *
+ * Unlike the reference (no status, exit(1) on OOM, image.c:17-28) every call
+ * returns an int status and never exits.  A context is bound to one CUDA
+ * device and one stream; all work is asynchronous on that stream unless the
+ * call copies to pageable host memory.  `frames` is the batch dimension that
+ * sits BELOW the reference API: one context processes frame pairs
+ * [0, max_frames) per launch.
+ *
+ * Arithmetic contract: IEEE binary32, no FMA contraction, expression order of
+ * the reference, so results are bitwise equal to the reference CPU build on
+ * the same inputs (tests/test_gpu_parity.py).
+ */
+#ifndef OFDIS_B200_H
+#define OFDIS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ofdis_ctx ofdis_ctx;
+
+/* The 21 run-time scalars of OFClass's constructor (oflow.h:93-111), CLI
+ * semantics of run_dense.cpp:225-294.  dp_thresh is the un-squared CLI value. */
+typedef struct ofdis_params {
+  int sc_f, sc_l;          /* first (coarsest) / last (finest) pyramid level */
+  int max_iter, min_iter;  /* Gauss-Newton iterations per patch */
+  float dp_thresh, dr_thresh, res_thresh;
+  int p_samp_s;            /* patch edge length P (even, P*P*noc % 4 == 0) */
+  float patove;            /* patch overlap in [0,1) */
+  int usefbcon;            /* forward-backward merge: must be 0 */
+  int costfct;             /* 0 L2, 1 L1, 2 pseudo-Huber */
+  int noc;                 /* image channels: 1 or 3 */
+  int patnorm;             /* mean-normalise patches */
+  int usetvref;            /* run the variational refinement */
+  float tv_alpha, tv_gamma, tv_delta;
+  int tv_innerit, tv_solverit;
+  float tv_sor;
+  int verbosity;
+} ofdis_params;
+
+enum {
+  OFDIS_OK = 0,
+  OFDIS_ERR_ARG = -1,         /* bad argument / unsupported geometry */
+  OFDIS_ERR_CUDA = -2,        /* a CUDA call failed; see ofdis_last_error */
+  OFDIS_ERR_UNSUPPORTED = -3, /* valid in the reference but not built here (usefbcon) */
+  OFDIS_ERR_NOMEM = -4
+};
+enum { OFDIS_MEM_HOST = 0, OFDIS_MEM_DEVICE = 1 };
+
+/* nop: 2 = optical flow (run_OF_*), 1 = stereo disparity (run_DE_*).
+ * width/height: level-0 size, divisible by 2^sc_f (oflow.h:87).  imgpadding:
+ * border of every level image (run_dense.cpp:343 passes the patch size).
+ * stream: a cudaStream_t to enqueue on, or NULL for a private stream. */
+int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* prm, int nop,
+                 int width, int height, int imgpadding, int max_frames);
+int ofdis_destroy(ofdis_ctx* ctx);
+const char* ofdis_last_error(const ofdis_ctx* ctx);
+const char* ofdis_version(void);
+
+/* level geometry (oflow.cpp:142-151, patchgrid.cpp:42-48) */
+int ofdis_level_info(const ofdis_ctx* ctx, int level, int* w, int* h, int* nopw, int* noph, int* steps);
+
+/* Images of one level of one frame pair: padded, row-major, channel-interleaved
+ * float32, (h+2*pad) x (w+2*pad) x noc, exactly what OFClass receives
+ * (oflow.h:84-86).  The gradients of I1 are never read by the reference
+ * (patch.cpp:90-97) and are not part of this interface. */
+int ofdis_upload_level(ofdis_ctx* ctx, int frame, int level, const float* i0, const float* i0x,
+                       const float* i0y, const float* i1, int memkind);
+
+/* Packed transfer: all levels sc_f..sc_l of frames [f0,f1) in the context's own
+ * layout (per frame: for level = sc_f down to sc_l: I0, I0x, I0y, I1), one copy. */
+size_t ofdis_packed_frame_floats(const ofdis_ctx* ctx);
+size_t ofdis_packed_offset(const ofdis_ctx* ctx, int level, int which /*0 I0,1 I0x,2 I0y,3 I1*/);
+int ofdis_upload_packed(ofdis_ctx* ctx, int f0, int f1, const float* packed, int memkind);
+
+/* Stage operators on frames [f0,f1) of one level. */
+int ofdis_patgrid_optimize(ofdis_ctx* ctx, int level, int f0, int f1, int init_from_coarser);
+int ofdis_patgrid_aggregate(ofdis_ctx* ctx, int level, int f0, int f1);
+int ofdis_varref_refine(ofdis_ctx* ctx, int level, int f0, int f1);
+
+/* Whole coarse-to-fine run on frames [0,nframes): == OFClass ctor per frame.
+ * use_initflow != 0 takes the flow stored at level sc_f+1 (ofdis_set_flow) as
+ * the reference's `initflow` argument. */
+int ofdis_run(ofdis_ctx* ctx, int nframes, int use_initflow);
+int ofdis_sync(ofdis_ctx* ctx);
+
+/* Dense flow of a level, (h x w x nop) interleaved float32.  Levels sc_l..sc_f+1
+ * are addressable (sc_f+1 only as initflow). */
+int ofdis_get_flow(ofdis_ctx* ctx, int frame, int level, float* dst, int memkind);
+int ofdis_set_flow(ofdis_ctx* ctx, int frame, int level, const float* src, int memkind);
+/* Final flow (level sc_l) of frames [f0,f1), contiguous, one copy. */
+int ofdis_get_flow_batch(ofdis_ctx* ctx, int f0, int f1, float* dst, int memkind);
+
+/* Per-patch results of the last ofdis_patgrid_optimize on `level` (any pointer may be
+ * NULL): p[np*nop] displacement, pweight[np*novals] abs. residual, conv[np], cnt[np]. */
+int ofdis_get_patches(ofdis_ctx* ctx, int frame, int level, float* p, float* pweight, int* conv,
+                      int* cnt);
+
+/* Test hook: raw internal planes of the last ofdis_varref_refine / debug run.
+ * name in {"Ix","Iy","Iz","Ixx","Ixy","Iyy","Ixz","Iyz","mask","rec","dudv"};
+ * returns the number of floats written (or a negative status). */
+long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, size_t max_floats);
+/* Test hook: run only the first n_inner inner iterations of the refinement. */
+int ofdis_debug_varref_iters(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner);
+
+/* Number of kernels this library has launched on the context since creation. */
+long ofdis_launch_count(const ofdis_ctx* ctx);
+/* CUDA-graph replay of ofdis_run (captured on first use per nframes). */
+int ofdis_set_graph_mode(ofdis_ctx* ctx, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,460 @@
+// C-ABI of libofdis_b200 (include/ofdis_b200.h): context, device workspaces,
+// level loop (OFClass::OFClass, oflow.cpp:76-108,138-157,184-295) and transfers.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ofdis_b200.h"
+#include "ofdis_internal.cuh"
+
+using namespace ofdis;
+
+struct ofdis_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  ofdis_params prm{};
+  int nop = 2, width = 0, height = 0, pad = 0, max_frames = 0;
+  int nlev = 0;                    // sc_f - sc_l + 1
+  std::vector<LevelGeom> lev;      // index: level - sc_l
+  std::vector<size_t> img_off;     // [lev][4] offsets (floats) inside one packed frame
+  size_t frame_floats = 0;
+  float* d_img = nullptr;          // [max_frames][frame_floats]
+  std::vector<float*> d_flow;      // index level - sc_l, plus one extra entry for level sc_f+1 (initflow)
+  std::vector<size_t> flow_floats;
+  VarRefPlanes planes{};
+  float* d_planes = nullptr;
+  PatchParams pp{};
+  long launches = 0;
+  int last_vr_level = -1, last_vr_f0 = 0;
+  bool graph_mode = false;
+  std::map<long, cudaGraphExec_t> graphs;
+  std::map<long, long> graph_launches;
+  std::string err;
+};
+
+namespace {
+
+int fail(ofdis_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (c) {
+    c->err = what;
+    if (e != cudaSuccess) {
+      c->err += ": ";
+      c->err += cudaGetErrorString(e);
+    }
+  }
+  return code;
+}
+
+#define CK(call)                                                        \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return fail(ctx, OFDIS_ERR_CUDA, #call, e__); \
+  } while (0)
+
+// camparam / optparam derivation (oflow.cpp:81-92,142-157; patchgrid.cpp:42-48)
+void make_level(LevelGeom& L, const ofdis_ctx* c, int sl) {
+  const ofdis_params& p = c->prm;
+  const float sc_fct = (float)pow(2, -sl);
+  L.h = (int)(c->height * sc_fct);
+  L.w = (int)(c->width * sc_fct);
+  L.pad = c->pad;
+  L.tmp_w = L.w + 2 * c->pad;
+  L.tmp_h = L.h + 2 * c->pad;
+  L.noc = p.noc;
+  L.nop = c->nop;
+  L.P = p.p_samp_s;
+  L.novals = p.noc * p.p_samp_s * p.p_samp_s;
+  L.steps = (int)floor(p.p_samp_s * (1 - p.patove));
+  if (L.steps < 1) L.steps = 1;
+  L.nopw = (int)ceil((float)L.w / (float)L.steps);
+  L.noph = (int)ceil((float)L.h / (float)L.steps);
+  L.np = L.nopw * L.noph;
+  L.offw = (L.w - (L.nopw - 1) * L.steps) / 2;
+  L.offh = (L.h - (L.noph - 1) * L.steps) / 2;
+  L.level = sl;
+  L.camlr = 0;
+  L.pitch = ((L.w + 3) / 4) * 4;
+  L.lb = -(float)p.p_samp_s / 2;
+  L.ubw = (float)(L.w + p.p_samp_s / 2 - 2);
+  L.ubh = (float)(L.h + p.p_samp_s / 2 - 2);
+  L.outlierthresh = (float)p.p_samp_s / 2;
+}
+
+LevelGeom* level_of(ofdis_ctx* c, int level) {
+  if (level < c->prm.sc_l || level > c->prm.sc_f) return nullptr;
+  return &c->lev[level - c->prm.sc_l];
+}
+
+cudaMemcpyKind kind_in(int memkind) { return memkind == OFDIS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
+cudaMemcpyKind kind_out(int memkind) { return memkind == OFDIS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
+
+int run_levels(ofdis_ctx* ctx, int nframes, int use_initflow) {
+  for (int sl = ctx->prm.sc_f; sl >= ctx->prm.sc_l; --sl) {
+    const bool from_coarser = (sl < ctx->prm.sc_f) || use_initflow;
+    int rc = ofdis_patgrid_optimize(ctx, sl, 0, nframes, from_coarser ? 1 : 0);
+    if (rc) return rc;
+    rc = ofdis_patgrid_aggregate(ctx, sl, 0, nframes);
+    if (rc) return rc;
+    if (ctx->prm.usetvref) {
+      rc = ofdis_varref_refine(ctx, sl, 0, nframes);
+      if (rc) return rc;
+    }
+  }
+  return OFDIS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ofdis_version(void) { return "ofdis_b200 0.1 (sm_100a)"; }
+
+const char* ofdis_last_error(const ofdis_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* prm, int nop, int width,
+                 int height, int imgpadding, int max_frames) {
+  if (!out || !prm) return OFDIS_ERR_ARG;
+  *out = nullptr;
+  if (prm->usefbcon) return OFDIS_ERR_UNSUPPORTED;
+  if (nop != 1 && nop != 2) return OFDIS_ERR_ARG;
+  if (prm->noc != 1 && prm->noc != 3) return OFDIS_ERR_ARG;
+  if (prm->sc_l < 0 || prm->sc_f < prm->sc_l || prm->sc_f > 16) return OFDIS_ERR_ARG;
+  if (prm->p_samp_s < 2 || (prm->p_samp_s & 1) || (prm->noc * prm->p_samp_s * prm->p_samp_s) % 4) return OFDIS_ERR_ARG;
+  if (imgpadding < prm->p_samp_s) return OFDIS_ERR_ARG;  // window of a patch at the bounds must stay inside the padding
+  if (width <= 0 || height <= 0 || (width % (1 << prm->sc_f)) || (height % (1 << prm->sc_f))) return OFDIS_ERR_ARG;
+  if (max_frames < 1 || prm->max_iter < 0) return OFDIS_ERR_ARG;
+  if (prm->usetvref && ((height >> prm->sc_f) < 4 || (width >> prm->sc_f) < 2)) return OFDIS_ERR_ARG;  // image.c:401-434 needs >= 4 rows
+  if (prm->usetvref && (height >> prm->sc_l) > 1024) return OFDIS_ERR_UNSUPPORTED;  // one SOR thread per row
+
+  ofdis_ctx* ctx = new (std::nothrow) ofdis_ctx();
+  if (!ctx) return OFDIS_ERR_NOMEM;
+  ctx->device = device;
+  ctx->prm = *prm;
+  ctx->nop = nop;
+  ctx->width = width;
+  ctx->height = height;
+  ctx->pad = imgpadding;
+  ctx->max_frames = max_frames;
+  ctx->nlev = prm->sc_f - prm->sc_l + 1;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return OFDIS_ERR_CUDA;
+  }
+  if (stream) ctx->stream = (cudaStream_t)stream;
+  else {
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete ctx;
+      return OFDIS_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+  }
+  ctx->pp.max_iter = prm->max_iter;
+  ctx->pp.min_iter = prm->min_iter;
+  ctx->pp.costfct = prm->costfct;
+  ctx->pp.patnorm = prm->patnorm;
+  ctx->pp.dp_thresh_sq = prm->dp_thresh * prm->dp_thresh;  // oflow.cpp:88
+  ctx->pp.dr_thresh = prm->dr_thresh;
+  ctx->pp.res_thresh = prm->res_thresh;
+
+  // geometry + packed image layout: per frame, level sc_f down to sc_l, I0 I0x I0y I1
+  ctx->lev.resize(ctx->nlev);
+  ctx->img_off.resize((size_t)ctx->nlev * 4);
+  size_t off = 0;
+  for (int sl = prm->sc_f; sl >= prm->sc_l; --sl) {
+    LevelGeom& L = ctx->lev[sl - prm->sc_l];
+    make_level(L, ctx, sl);
+    const size_t n = (size_t)L.tmp_w * L.tmp_h * L.noc;
+    for (int k = 0; k < 4; ++k) {
+      ctx->img_off[(size_t)(sl - prm->sc_l) * 4 + k] = off;
+      off += (n + 3) / 4 * 4;  // keep every array 16-byte aligned
+    }
+  }
+  ctx->frame_floats = off;
+
+  auto dalloc = [&](void** p, size_t bytes) -> bool {
+    return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess;
+  };
+  bool ok = dalloc((void**)&ctx->d_img, sizeof(float) * ctx->frame_floats * max_frames);
+  ctx->d_flow.assign(ctx->nlev + 1, nullptr);
+  ctx->flow_floats.assign(ctx->nlev + 1, 0);
+  for (int li = 0; li <= ctx->nlev && ok; ++li) {
+    const int sl = prm->sc_l + li;
+    const size_t n = (size_t)(width >> sl) * (height >> sl) * nop;
+    ctx->flow_floats[li] = n;
+    ok = dalloc((void**)&ctx->d_flow[li], sizeof(float) * n * max_frames);
+    if (ok) cudaMemsetAsync(ctx->d_flow[li], 0, sizeof(float) * n * max_frames, ctx->stream);
+  }
+  for (int li = 0; li < ctx->nlev && ok; ++li) {
+    LevelGeom& L = ctx->lev[li];
+    for (int k = 0; k < 4; ++k) L.img[k] = ctx->d_img + ctx->img_off[(size_t)li * 4 + k];
+    L.img_frame_stride = ctx->frame_floats;
+    L.flow = ctx->d_flow[li];
+    L.flow_frame_stride = ctx->flow_floats[li];
+    L.flow_prev = ctx->d_flow[li + 1];
+    L.flow_prev_frame_stride = ctx->flow_floats[li + 1];
+    ok = ok && dalloc((void**)&L.pat_p, sizeof(float) * L.np * nop * max_frames);
+    ok = ok && dalloc((void**)&L.pat_w, sizeof(float) * (size_t)L.np * L.novals * max_frames);
+    ok = ok && dalloc((void**)&L.pat_conv, sizeof(int) * L.np * max_frames);
+    ok = ok && dalloc((void**)&L.pat_cnt, sizeof(int) * L.np * max_frames);
+  }
+  if (ok && prm->usetvref) {
+    // refinement planes sized for the finest level: mask, avg[C], 8 x deriv[C], dudv (2), rec (8)
+    const LevelGeom& Lf = ctx->lev[0];
+    const size_t plane = (size_t)Lf.pitch * Lf.h;
+    const int C = prm->noc;
+    const size_t per_frame = plane * (1 + C + 8 * C + 2 + 8);
+    ok = dalloc((void**)&ctx->d_planes, sizeof(float) * per_frame * max_frames);
+    if (ok) {
+      float* q = ctx->d_planes;
+      VarRefPlanes& P = ctx->planes;
+      P.rec = reinterpret_cast<float4*>(q); q += plane * 8 * max_frames;   // 32-byte records first (alignment)
+      P.dudv = reinterpret_cast<float2*>(q); q += plane * 2 * max_frames;
+      P.mask = q; q += plane * max_frames;
+      P.avg = q; q += plane * C * max_frames;
+      for (int k = 0; k < 8; ++k) { P.deriv[k] = q; q += plane * C * max_frames; }
+      P.plane = plane;
+    }
+  }
+  if (!ok) {
+    ofdis_destroy(ctx);
+    return OFDIS_ERR_NOMEM;
+  }
+  *out = ctx;
+  return OFDIS_OK;
+}
+
+int ofdis_destroy(ofdis_ctx* ctx) {
+  if (!ctx) return OFDIS_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  cudaFree(ctx->d_img);
+  for (float* p : ctx->d_flow) cudaFree(p);
+  for (LevelGeom& L : ctx->lev) {
+    cudaFree(L.pat_p);
+    cudaFree(L.pat_w);
+    cudaFree(L.pat_conv);
+    cudaFree(L.pat_cnt);
+  }
+  cudaFree(ctx->d_planes);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return OFDIS_OK;
+}
+
+int ofdis_level_info(const ofdis_ctx* ctx, int level, int* w, int* h, int* nopw, int* noph, int* steps) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  const LevelGeom* L = level_of(const_cast<ofdis_ctx*>(ctx), level);
+  if (!L) return OFDIS_ERR_ARG;
+  if (w) *w = L->w;
+  if (h) *h = L->h;
+  if (nopw) *nopw = L->nopw;
+  if (noph) *noph = L->noph;
+  if (steps) *steps = L->steps;
+  return OFDIS_OK;
+}
+
+int ofdis_upload_level(ofdis_ctx* ctx, int frame, int level, const float* i0, const float* i0x,
+                       const float* i0y, const float* i1, int memkind) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  LevelGeom* L = level_of(ctx, level);
+  if (!L || frame < 0 || frame >= ctx->max_frames || !i0 || !i0x || !i0y || !i1) return fail(ctx, OFDIS_ERR_ARG, "upload_level: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)L->tmp_w * L->tmp_h * L->noc;
+  const float* src[4] = {i0, i0x, i0y, i1};
+  for (int k = 0; k < 4; ++k)
+    CK(cudaMemcpyAsync(const_cast<float*>(L->img[k]) + (size_t)frame * ctx->frame_floats, src[k], sizeof(float) * n,
+                       kind_in(memkind), ctx->stream));
+  return OFDIS_OK;
+}
+
+size_t ofdis_packed_frame_floats(const ofdis_ctx* ctx) { return ctx ? ctx->frame_floats : 0; }
+
+size_t ofdis_packed_offset(const ofdis_ctx* ctx, int level, int which) {
+  if (!ctx || level < ctx->prm.sc_l || level > ctx->prm.sc_f || which < 0 || which > 3) return (size_t)-1;
+  return ctx->img_off[(size_t)(level - ctx->prm.sc_l) * 4 + which];
+}
+
+int ofdis_upload_packed(ofdis_ctx* ctx, int f0, int f1, const float* packed, int memkind) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  if (f0 < 0 || f1 > ctx->max_frames || f0 >= f1 || !packed) return fail(ctx, OFDIS_ERR_ARG, "upload_packed: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->d_img + (size_t)f0 * ctx->frame_floats, packed,
+                     sizeof(float) * ctx->frame_floats * (f1 - f0), kind_in(memkind), ctx->stream));
+  return OFDIS_OK;
+}
+
+int ofdis_patgrid_optimize(ofdis_ctx* ctx, int level, int f0, int f1, int init_from_coarser) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  LevelGeom* L = level_of(ctx, level);
+  if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_optimize: bad argument");
+  const int n = launch_patch_optimize(*L, ctx->pp, f0, f1, init_from_coarser != 0, ctx->stream);
+  if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "patch_optimize_kernel launch", cudaGetLastError());
+  ctx->launches += n;
+  return OFDIS_OK;
+}
+
+int ofdis_patgrid_aggregate(ofdis_ctx* ctx, int level, int f0, int f1) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  LevelGeom* L = level_of(ctx, level);
+  if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_aggregate: bad argument");
+  const int n = launch_densify(*L, f0, f1, ctx->stream);
+  if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "densify_kernel launch", cudaGetLastError());
+  ctx->launches += n;
+  return OFDIS_OK;
+}
+
+static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_override) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  LevelGeom* L = level_of(ctx, level);
+  if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "varref_refine: bad argument");
+  if (!ctx->d_planes) return fail(ctx, OFDIS_ERR_ARG, "varref_refine: context created with usetvref=0");
+  VarRefParams vp;
+  // refine_variational.cpp:36-43
+  vp.n_inner = n_inner_override >= 0 ? n_inner_override : ctx->prm.tv_innerit * (level + 1);
+  vp.n_solver = ctx->prm.tv_solverit;
+  vp.omega = ctx->prm.tv_sor;
+  vp.quarter_alpha = 0.25f * ctx->prm.tv_alpha;
+  vp.half_gamma_over3 = ctx->prm.tv_gamma * 0.5f / 3.0f;
+  vp.half_delta_over3 = ctx->prm.tv_delta * 0.5f / 3.0f;
+  VarRefPlanes pl = ctx->planes;
+  pl.plane = (size_t)L->pitch * L->h;
+  const int n = launch_varref(*L, pl, vp, f0, f1, ctx->stream);
+  if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "varref kernels launch", cudaGetLastError());
+  ctx->launches += n;
+  ctx->last_vr_level = level;
+  ctx->last_vr_f0 = f0;
+  return OFDIS_OK;
+}
+
+int ofdis_varref_refine(ofdis_ctx* ctx, int level, int f0, int f1) { return varref_impl(ctx, level, f0, f1, -1); }
+
+int ofdis_debug_varref_iters(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner) {
+  return varref_impl(ctx, level, f0, f1, n_inner);
+}
+
+int ofdis_set_graph_mode(ofdis_ctx* ctx, int enabled) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  ctx->graph_mode = enabled != 0;
+  return OFDIS_OK;
+}
+
+int ofdis_run(ofdis_ctx* ctx, int nframes, int use_initflow) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  if (nframes < 1 || nframes > ctx->max_frames) return fail(ctx, OFDIS_ERR_ARG, "run: bad frame count");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->graph_mode) return run_levels(ctx, nframes, use_initflow);
+  const long key = (long)nframes * 2 + (use_initflow ? 1 : 0);
+  auto it = ctx->graphs.find(key);
+  if (it == ctx->graphs.end()) {
+    const long before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_levels(ctx, nframes, use_initflow);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ctx, OFDIS_ERR_CUDA, "cudaStreamEndCapture", e);
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(ctx, OFDIS_ERR_CUDA, "cudaGraphInstantiate", e);
+    ctx->graph_launches[key] = ctx->launches - before;
+    ctx->launches = before;  // capture does not execute
+    it = ctx->graphs.emplace(key, exec).first;
+  }
+  CK(cudaGraphLaunch(it->second, ctx->stream));
+  ctx->launches += ctx->graph_launches[key];
+  return OFDIS_OK;
+}
+
+int ofdis_sync(ofdis_ctx* ctx) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return OFDIS_OK;
+}
+
+static int flow_index(const ofdis_ctx* ctx, int level) {
+  if (level < ctx->prm.sc_l || level > ctx->prm.sc_f + 1) return -1;
+  return level - ctx->prm.sc_l;
+}
+
+int ofdis_get_flow(ofdis_ctx* ctx, int frame, int level, float* dst, int memkind) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  const int li = flow_index(ctx, level);
+  if (li < 0 || frame < 0 || frame >= ctx->max_frames || !dst) return fail(ctx, OFDIS_ERR_ARG, "get_flow: bad argument");
+  CK(cudaMemcpyAsync(dst, ctx->d_flow[li] + (size_t)frame * ctx->flow_floats[li], sizeof(float) * ctx->flow_floats[li],
+                     kind_out(memkind), ctx->stream));
+  if (memkind == OFDIS_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+  return OFDIS_OK;
+}
+
+int ofdis_set_flow(ofdis_ctx* ctx, int frame, int level, const float* src, int memkind) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  const int li = flow_index(ctx, level);
+  if (li < 0 || frame < 0 || frame >= ctx->max_frames || !src) return fail(ctx, OFDIS_ERR_ARG, "set_flow: bad argument");
+  CK(cudaMemcpyAsync(ctx->d_flow[li] + (size_t)frame * ctx->flow_floats[li], src, sizeof(float) * ctx->flow_floats[li],
+                     kind_in(memkind), ctx->stream));
+  return OFDIS_OK;
+}
+
+int ofdis_get_flow_batch(ofdis_ctx* ctx, int f0, int f1, float* dst, int memkind) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  if (f0 < 0 || f1 > ctx->max_frames || f0 >= f1 || !dst) return fail(ctx, OFDIS_ERR_ARG, "get_flow_batch: bad argument");
+  CK(cudaMemcpyAsync(dst, ctx->d_flow[0] + (size_t)f0 * ctx->flow_floats[0], sizeof(float) * ctx->flow_floats[0] * (f1 - f0),
+                     kind_out(memkind), ctx->stream));
+  return OFDIS_OK;
+}
+
+int ofdis_get_patches(ofdis_ctx* ctx, int frame, int level, float* p, float* pweight, int* conv, int* cnt) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  LevelGeom* L = level_of(ctx, level);
+  if (!L || frame < 0 || frame >= ctx->max_frames) return fail(ctx, OFDIS_ERR_ARG, "get_patches: bad argument");
+  const size_t np = L->np;
+  if (p) CK(cudaMemcpyAsync(p, L->pat_p + frame * np * L->nop, sizeof(float) * np * L->nop, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pweight) CK(cudaMemcpyAsync(pweight, L->pat_w + frame * np * L->novals, sizeof(float) * np * L->novals, cudaMemcpyDeviceToHost, ctx->stream));
+  if (conv) CK(cudaMemcpyAsync(conv, L->pat_conv + frame * np, sizeof(int) * np, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cnt) CK(cudaMemcpyAsync(cnt, L->pat_cnt + frame * np, sizeof(int) * np, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return OFDIS_OK;
+}
+
+long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, size_t max_floats) {
+  if (!ctx || !name || !dst || ctx->last_vr_level < 0) return OFDIS_ERR_ARG;
+  LevelGeom* L = level_of(ctx, ctx->last_vr_level);
+  const int fr = frame - ctx->last_vr_f0;
+  if (!L || fr < 0) return OFDIS_ERR_ARG;
+  const size_t plane = (size_t)L->pitch * L->h;
+  const int C = L->noc;
+  static const char* dn[8] = {"Ix", "Iy", "Iz", "Ixx", "Ixy", "Iyy", "Ixz", "Iyz"};
+  const float* src = nullptr;
+  size_t n = 0;
+  for (int k = 0; k < 8; ++k)
+    if (!strcmp(name, dn[k])) {
+      src = ctx->planes.deriv[k] + (size_t)fr * C * plane;
+      n = plane * C;
+    }
+  if (!strcmp(name, "mask")) { src = ctx->planes.mask + (size_t)fr * plane; n = plane; }
+  if (!strcmp(name, "dudv")) { src = reinterpret_cast<const float*>(ctx->planes.dudv + (size_t)fr * plane); n = plane * 2; }
+  if (!strcmp(name, "rec")) {
+    const int rf = (L->nop == 2) ? 8 : 4;
+    src = reinterpret_cast<const float*>(ctx->planes.rec) + (size_t)fr * plane * rf;
+    n = plane * rf;
+  }
+  if (!src || n > max_floats) return OFDIS_ERR_ARG;
+  if (cudaMemcpyAsync(dst, src, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return OFDIS_ERR_CUDA;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return OFDIS_ERR_CUDA;
+  return (long)n;
+}
+
+long ofdis_launch_count(const ofdis_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

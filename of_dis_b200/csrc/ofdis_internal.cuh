@@ -1,0 +1,63 @@
+// Internal declarations shared by the CUDA translation units of libofdis_b200.
+// sm_100a only; compiled with -fmad=false (no FMA contraction) because results
+// must be bitwise equal to the reference CPU build.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ofdis {
+
+// Per-level geometry, mirrors camparam/optparam (oflow.h:16-76) + grid (patchgrid.cpp:42-48).
+struct LevelGeom {
+  int w, h, pad, tmp_w, tmp_h;
+  int noc, nop, P, novals, steps, nopw, noph, np, offw, offh;
+  int level, camlr;
+  int pitch;               // row pitch (floats) of the planar refinement planes, multiple of 4
+  float lb, ubw, ubh, outlierthresh;
+  // device pointers (frame 0); frame f adds f * stride
+  const float* img[4];     // I0, I0x, I0y, I1 (padded, interleaved)
+  size_t img_frame_stride; // floats between consecutive frames in the packed image buffer
+  float* flow;             // [frames][h][w][nop]
+  size_t flow_frame_stride;
+  const float* flow_prev;  // level+1 flow (or initflow), nullptr -> zero init
+  size_t flow_prev_frame_stride;
+  float* pat_p;            // [frames][np][nop]
+  float* pat_w;            // [frames][np][novals]
+  int* pat_conv;           // [frames][np]
+  int* pat_cnt;            // [frames][np]
+};
+
+struct PatchParams {
+  int max_iter, min_iter, costfct, patnorm;
+  float dp_thresh_sq, dr_thresh, res_thresh;
+};
+
+// Refinement workspace for one level (all frames), planar planes of pitch*h floats.
+struct VarRefPlanes {
+  float* mask;             // [frames]
+  float* avg;              // [frames][C]   0.5*(I1w+I0)            (setup only)
+  float* deriv[8];         // Ix Iy Iz Ixx Ixy Iyy Ixz Iyz, each [frames][C]
+  float2* dudv;            // [frames] interleaved (du,dv); stereo uses .x
+  float4* rec;             // [frames] SOR records, 2 x float4 per pixel (flow) / 1 (stereo)
+  size_t plane;            // pitch*h
+};
+
+struct VarRefParams {
+  float quarter_alpha, half_gamma_over3, half_delta_over3, omega;
+  int n_inner, n_solver;
+};
+
+// launchers (each returns the number of kernels launched, <0 on error)
+int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int f1, bool init_from_coarser,
+                          cudaStream_t st);
+int launch_densify(const LevelGeom& g, int f0, int f1, cudaStream_t st);
+int launch_varref(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
+                  cudaStream_t st);
+
+// ---- exact-arithmetic helpers -------------------------------------------------
+// std::min/std::max semantics of the reference (operand order matters for +-0/NaN)
+__device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }
+__device__ __forceinline__ int clampi(int v, int n) { return v < 0 ? 0 : (v > n - 1 ? n - 1 : v); }
+
+}  // namespace ofdis

@@ -1,0 +1,375 @@
+// Patch stage of the DIS hot path on sm_100a: K1 (template + Hessian), K2 (init
+// from the coarser flow), K3 (inverse-compositional Gauss-Newton iterations)
+// fused in one kernel, and K4 (densification) as a deterministic gather.
+//
+// Reference: PatClass / PatGridClass (patch.cpp:57-402, patchgrid.cpp:98-397).
+//
+// Mapping.  The reference reduces every P*P*C-vector with 8 strided partial
+// sums (element e goes to partial e mod 8, added in increasing e) that are then
+// folded 8 -> 4 -> 2 -> 1 (oracle/eigen_shim/Eigen/Core).  To be bit-identical
+// the kernel gives one patch to a group of 8 lanes: lane l owns the elements
+// e = l, l+8, l+16, ... and the fold is three xor-shuffles (4, 2, 1).  Four
+// patches share a warp; a CTA of 256 threads holds 32 patches.  The template,
+// its gradients and the residual of each lane live in shared memory as
+// [slot][thread] columns (conflict free, private to the thread), staged once.
+// The bilinear taps of I1 are plain LDGs: the (P+1)x(P+1) window of a patch
+// moves by a fraction of a pixel per iteration and stays L1-resident.
+#include "ofdis_internal.cuh"
+
+namespace ofdis {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// fold of the 8 partial sums of one patch (lanes l..l+7 of an aligned group)
+__device__ __forceinline__ float fold8(float acc, float tailv, bool has_strided, bool has_tail) {
+  float s;
+  const float other = __shfl_xor_sync(FULL, acc, 4);
+  if (has_strided) {
+    s = acc + other;
+    if (has_tail) s = s + tailv;
+  } else {
+    s = tailv;
+  }
+  const float t = s + __shfl_xor_sync(FULL, s, 2);
+  return t + __shfl_xor_sync(FULL, t, 1);
+}
+
+template <int NOP>
+__global__ void __launch_bounds__(256) patch_optimize_kernel(LevelGeom g, PatchParams pp, int f0,
+                                                              int init_from_coarser) {
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int l8 = tid & 7;
+  const int frame = f0 + blockIdx.y;
+  const int ip = blockIdx.x * (nthr >> 3) + (tid >> 3);
+  const bool valid = ip < g.np;
+
+  const int P = g.P, C = g.noc, n = g.novals;
+  const int n8 = (n >> 3) << 3, nk = n8 >> 3;
+  const bool has_tail = (n - n8) >= 4, has_strided = nk > 0;
+  const int NK = nk + (has_tail ? 1 : 0);
+  const float fn = (float)n;
+
+  float* sT = smem + tid;
+  float* sGx = sT + NK * nthr;
+  float* sGy = sGx + NK * nthr;
+  float* sD = sGy + NK * nthr;
+  int* sOff = reinterpret_cast<int*>(sD + NK * nthr);
+  const int rowC = g.tmp_w * C;
+
+  const float* i0 = g.img[0] + (size_t)frame * g.img_frame_stride;
+  const float* i0x = g.img[1] + (size_t)frame * g.img_frame_stride;
+  const float* i0y = g.img[2] + (size_t)frame * g.img_frame_stride;
+  const float* i1 = g.img[3] + (size_t)frame * g.img_frame_stride;
+
+  // ---- patch geometry (patchgrid.cpp:62-69) ---------------------------------
+  const int ipc = valid ? ip : 0;
+  const int gx_i = ipc / g.noph, gy_i = ipc - gx_i * g.noph;
+  const int cxi = gx_i * g.steps + g.offw, cyi = gy_i * g.steps + g.offh;
+  const float refx = (float)cxi, refy = (float)cyi;
+
+  // ---- K1: template, gradients, mean normalisation (patch.cpp:287-332) ------
+  {
+    const int base = ((cxi + g.pad - P / 2) + (cyi + g.pad - P / 2) * g.tmp_w) * C;
+    float acc = 0.f, tailv = 0.f;
+    for (int k = 0; k < NK; ++k) {
+      const int e = (k < nk) ? (l8 + 8 * k) : (n8 + (l8 & 3));
+      const int y = e / (P * C), rem = e - y * (P * C), x = rem / C, c = rem - x * C;
+      const int off = y * rowC + x * C + c;
+      sOff[k * nthr] = off;
+      const float t = i0[base + off];
+      sT[k * nthr] = t;
+      sGx[k * nthr] = i0x[base + off];
+      sGy[k * nthr] = i0y[base + off];
+      if (k < nk) acc = (k == 0) ? t : acc + t;
+      else tailv = t;
+    }
+    if (pp.patnorm > 0) {
+      const float m = fold8(acc, tailv, has_strided, has_tail) / fn;
+      for (int k = 0; k < NK; ++k) sT[k * nthr] = sT[k * nthr] - m;
+    }
+  }
+
+  // ---- Hessian and its Cholesky factor (patch.cpp:71-88, Eigen LLT) ---------
+  float L00, L10 = 0.f, L11 = 0.f;
+  {
+    float axx = 0.f, axy = 0.f, ayy = 0.f, txx = 0.f, txy = 0.f, tyy = 0.f;
+    for (int k = 0; k < NK; ++k) {
+      const float a = sGx[k * nthr], b = sGy[k * nthr];
+      const float vxx = a * a, vxy = a * b, vyy = b * b;
+      if (k < nk) {
+        axx = (k == 0) ? vxx : axx + vxx;
+        axy = (k == 0) ? vxy : axy + vxy;
+        ayy = (k == 0) ? vyy : ayy + vyy;
+      } else {
+        txx = vxx; txy = vxy; tyy = vyy;
+      }
+    }
+    float H00 = fold8(axx, txx, has_strided, has_tail);
+    if (NOP == 2) {
+      const float H01 = fold8(axy, txy, has_strided, has_tail);
+      float H11 = fold8(ayy, tyy, has_strided, has_tail);
+      if (H00 * H11 - H01 * H01 == 0.f) {
+        H00 = (float)((double)H00 + 1e-10);
+        H11 = (float)((double)H11 + 1e-10);
+      }
+      L00 = H00; L10 = H01; L11 = H11;
+      if (H00 > 0.f) {
+        L00 = sqrtf(H00);
+        L10 = H01 / L00;
+        const float x = H11 - L10 * L10;
+        if (x > 0.f) L11 = sqrtf(x);
+      }
+    } else {
+      if (H00 == 0.f) H00 = (float)((double)H00 + 1e-10);
+      L00 = H00 > 0.f ? sqrtf(H00) : H00;
+    }
+  }
+
+  // ---- K2: start value (patchgrid.cpp:195-211) ------------------------------
+  float pin0 = 0.f, pin1 = 0.f;
+  if (init_from_coarser && g.flow_prev != nullptr) {
+    const float* fp = g.flow_prev + (size_t)frame * g.flow_prev_frame_stride;
+    const int i = (cyi >> 1) * (g.w / 2) + (cxi >> 1);
+    if (NOP == 2) {
+      const float2 v = reinterpret_cast<const float2*>(fp)[i];
+      pin0 = v.x * 2.f;
+      pin1 = v.y * 2.f;
+    } else {
+      pin0 = fp[i] * 2.f;
+    }
+  }
+
+  // ---- K3: OptimizeStart / OptimizeIter (patch.cpp:119-212, 264-284) --------
+  float p0 = pin0, p1 = pin1, dp0 = 0.f, dp1 = 0.f;
+  float ptx = refx + p0, pty = (NOP == 2) ? refy + p1 : refy;
+  const float stx = ptx, sty = pty;
+  float dpsq_init = 1e-10f, mares = 1e5f, mares_old = 1e20f;
+  int cnt = 0, conv = 0;
+  bool wrote_w = false;   // whether the residual column holds a valid error image
+  bool finishing = false; // reset happened: one last error image, no test
+  bool active = valid;
+  if (active && (ptx < g.lb || pty < g.lb || ptx > g.ubw || pty > g.ubh)) {
+    conv = 1;  // patch.cpp:135-141 (pweight stays zero-initialised)
+    active = false;
+  }
+
+  while (__any_sync(FULL, active)) {
+    // -- error image at (ptx, pty): getPatchStaticBil + LossComputeErrorImage --
+    float b0 = 0.f, b1 = 0.f, sw = 0.f, tb0 = 0.f, tb1 = 0.f, tsw = 0.f;
+    {
+      float acc = 0.f, tailv = 0.f;
+      int base = 0;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+      if (active) {
+        const int pcx = (int)ceilf(ptx + .00001f), pcy = (int)ceilf(pty + .00001f);
+        const int pfx = (int)floorf(ptx), pfy = (int)floorf(pty);
+        const float rx = ptx - (float)pfx, ry = pty - (float)pfy;
+        w0 = rx * ry;
+        w1 = (1.f - rx) * ry;
+        w2 = rx * (1.f - ry);
+        w3 = (1.f - rx) * (1.f - ry);
+        base = ((pcx + g.pad - P / 2) + (pcy + g.pad - P / 2) * g.tmp_w) * C;
+        for (int k = 0; k < NK; ++k) {
+          const float* a = i1 + base + sOff[k * nthr];
+          const float v = w0 * __ldg(a) + w1 * __ldg(a - C) + w2 * __ldg(a - rowC) + w3 * __ldg(a - rowC - C);
+          sD[k * nthr] = v;
+          if (k < nk) acc = (k == 0) ? v : acc + v;
+          else tailv = v;
+        }
+      }
+      float m = 0.f;
+      if (pp.patnorm > 0) m = fold8(acc, tailv, has_strided, has_tail) / fn;
+      if (active) {
+        for (int k = 0; k < NK; ++k) {
+          float d = sD[k * nthr];
+          if (pp.patnorm > 0) d = d - m;
+          float r, w;
+          if (pp.costfct == 0) {
+            r = d - sT[k * nthr];
+            w = fabsf(r);
+          } else if (pp.costfct == 1) {
+            const float t = d - sT[k * nthr];
+            r = copysignf(sqrtf(fabsf(t)), t);
+            w = fabsf(r);
+          } else if (pp.costfct == 2) {
+            const float t = d - sT[k * nthr];
+            const float hh = sqrtf((sqrtf(1.0f + (t * t) / 25.0f) - 1.0f) * 50.0f);
+            r = copysignf(hh, t);
+            w = fabsf(r);
+          } else {  // reference leaves pdiff/pweight untouched (patch.cpp:230-261)
+            r = d;
+            w = 0.f;
+          }
+          sD[k * nthr] = r;
+          const float vx = sGx[k * nthr] * r, vy = sGy[k * nthr] * r;
+          if (k < nk) {
+            b0 = (k == 0) ? vx : b0 + vx;
+            b1 = (k == 0) ? vy : b1 + vy;
+            sw = (k == 0) ? w : sw + w;
+          } else {
+            tb0 = vx; tb1 = vy; tsw = w;
+          }
+        }
+        wrote_w = (pp.costfct >= 0 && pp.costfct <= 2);
+      }
+    }
+    b0 = fold8(b0, tb0, has_strided, has_tail);
+    if (NOP == 2) b1 = fold8(b1, tb1, has_strided, has_tail);
+    sw = fold8(sw, tsw, has_strided, has_tail);
+
+    if (active) {
+      if (finishing) {
+        active = false;
+      } else {
+        // OptimizeComputeErrImg tail (patch.cpp:272-282)
+        const float dpsq = (NOP == 2) ? dp0 * dp0 + dp1 * dp1 : dp0 * dp0;
+        if (cnt == 1) dpsq_init = dpsq;
+        mares_old = mares;
+        mares = sw / fn;
+        const bool go = (cnt < pp.max_iter) & (mares > pp.res_thresh) &
+                        ((cnt < pp.min_iter) | (dpsq / dpsq_init >= pp.dp_thresh_sq)) &
+                        ((cnt < pp.min_iter) | (mares / mares_old <= pp.dr_thresh));
+        if (!go) {
+          conv = 1;
+          active = false;
+        } else {
+          // one Gauss-Newton step (patch.cpp:174-208)
+          cnt++;
+          if (NOP == 2) {
+            const float y0 = b0 / L00;
+            const float y1 = (b1 - L10 * y0) / L11;
+            dp1 = y1 / L11;
+            dp0 = (y0 - L10 * dp1) / L00;
+            p0 = p0 - dp0;
+            p1 = p1 - dp1;
+            ptx = refx + p0;
+            pty = refy + p1;
+          } else {
+            dp0 = (b0 / L00) / L00;
+            p0 = p0 - dp0;
+            p0 = (g.camlr == 0) ? std_min(p0, 0.0f) : std_max(p0, 0.0f);
+            ptx = refx + p0;
+          }
+          const float ex = stx - ptx, ey = sty - pty;
+          if (sqrtf(ex * ex + ey * ey) > g.outlierthresh || ptx < g.lb || pty < g.lb || ptx > g.ubw ||
+              pty > g.ubh) {
+            p0 = pin0;
+            p1 = pin1;
+            ptx = refx + p0;
+            if (NOP == 2) pty = refy + p1;
+            conv = 1;
+            finishing = true;
+          }
+        }
+      }
+    }
+  }
+
+  if (valid) {
+    float* pw = g.pat_w + ((size_t)frame * g.np + ip) * n;
+    for (int k = 0; k < NK; ++k) {
+      if (k < nk) pw[l8 + 8 * k] = wrote_w ? fabsf(sD[k * nthr]) : 0.f;
+      else if (l8 < 4) pw[n8 + l8] = wrote_w ? fabsf(sD[k * nthr]) : 0.f;
+    }
+    if (l8 == 0) {
+      float* po = g.pat_p + ((size_t)frame * g.np + ip) * NOP;
+      po[0] = p0;
+      if (NOP == 2) po[1] = p1;
+      g.pat_conv[(size_t)frame * g.np + ip] = conv;
+      g.pat_cnt[(size_t)frame * g.np + ip] = cnt;
+    }
+  }
+}
+
+// K4: PatGridClass::AggregateFlowDense (patchgrid.cpp:213-275,377-394) as a
+// per-pixel gather.  The reference scatters patch by patch in ip = x*noph + y
+// order; visiting the covering patches of a pixel in ascending (x, y) grid order
+// performs the same float additions in the same order, without atomics.
+template <int NOP>
+__global__ void __launch_bounds__(256) densify_kernel(LevelGeom g, int f0) {
+  const int xi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yi = blockIdx.y * blockDim.y + threadIdx.y;
+  const int frame = f0 + blockIdx.z;
+  if (xi >= g.w || yi >= g.h) return;
+  const int P = g.P, C = g.noc, n = g.novals, hp = P / 2;
+  const float* pp = g.pat_p + (size_t)frame * g.np * NOP;
+  const float* pw = g.pat_w + (size_t)frame * g.np * n;
+  // grid columns whose patch covers xi: xi - hp + 1 <= cx <= xi + hp
+  int gx0 = (xi - hp + 1 - g.offw + g.steps - 1);
+  gx0 = gx0 < 0 ? 0 : gx0 / g.steps;
+  int gx1 = xi + hp - g.offw;
+  gx1 = gx1 < 0 ? -1 : gx1 / g.steps;
+  if (gx1 > g.nopw - 1) gx1 = g.nopw - 1;
+  int gy0 = (yi - hp + 1 - g.offh + g.steps - 1);
+  gy0 = gy0 < 0 ? 0 : gy0 / g.steps;
+  int gy1 = yi + hp - g.offh;
+  gy1 = gy1 < 0 ? -1 : gy1 / g.steps;
+  if (gy1 > g.noph - 1) gy1 = g.noph - 1;
+
+  float we = 0.f, a0 = 0.f, a1 = 0.f;
+  for (int gx = gx0; gx <= gx1; ++gx) {
+    const int cx = gx * g.steps + g.offw, rx = xi - cx + hp;
+    for (int gy = gy0; gy <= gy1; ++gy) {
+      const int cy = gy * g.steps + g.offh, ry = yi - cy + hp;
+      const int ip = gx * g.noph + gy;
+      float absw;
+      if (C == 1) {
+        absw = 1.0f / std_max(2.0f, pw[(size_t)ip * n + ry * P + rx]);
+      } else {
+        // patchgrid.cpp:243-259: the weight cursor advances by 1 for a patch pixel
+        // outside the image and by C for one inside.
+        const int x0 = cx - hp < 0 ? hp - cx : 0, y0 = cy - hp < 0 ? hp - cy : 0;
+        const int x1 = cx + hp - 1 > g.w - 1 ? g.w - 1 - cx + hp : P - 1;
+        const int inb = (ry - y0) * (x1 - x0 + 1) + (rx - x0);
+        const float* q = pw + (size_t)ip * n + (ry * P + rx) + (C - 1) * inb;
+        absw = std_max(2.0f, q[0]);
+        for (int c = 1; c < C; ++c) absw += std_max(2.0f, q[c]);
+        absw = 1.0f / absw;
+      }
+      we += absw;
+      a0 += pp[ip * NOP] * absw;
+      if (NOP == 2) a1 += pp[ip * NOP + 1] * absw;
+    }
+  }
+  float* out = g.flow + (size_t)frame * g.flow_frame_stride + ((size_t)yi * g.w + xi) * NOP;
+  if (we > 0.f) {
+    a0 = a0 / we;
+    a1 = a1 / we;
+  }
+  out[0] = a0;
+  if (NOP == 2) out[1] = a1;
+}
+
+}  // namespace
+
+int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int f1, bool init_from_coarser,
+                          cudaStream_t st) {
+  const int n = g.novals;
+  const int NK = (n / 8) + (((n % 8) >= 4) ? 1 : 0);
+  int threads = 256;
+  while (threads > 32 && (size_t)5 * NK * threads * sizeof(float) > 200 * 1024) threads >>= 1;
+  const size_t smem = (size_t)5 * NK * threads * sizeof(float);
+  const dim3 grid((g.np + threads / 8 - 1) / (threads / 8), f1 - f0);
+  if (g.nop == 2) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(patch_optimize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    patch_optimize_kernel<2><<<grid, threads, smem, st>>>(g, pp, f0, init_from_coarser ? 1 : 0);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(patch_optimize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    patch_optimize_kernel<1><<<grid, threads, smem, st>>>(g, pp, f0, init_from_coarser ? 1 : 0);
+  }
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_densify(const LevelGeom& g, int f0, int f1, cudaStream_t st) {
+  const dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8, f1 - f0);
+  if (g.nop == 2) densify_kernel<2><<<grid, block, 0, st>>>(g, f0);
+  else densify_kernel<1><<<grid, block, 0, st>>>(g, f0);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace ofdis

@@ -254,8 +254,9 @@ static void patch_optimize(const dis_level* L, const dis_params* prm, const floa
         float b0 = vdot(gx, pdiff, n);
         dp[0] = (b0 / H->L00) / H->L00;
         p[0] = p[0] - dp[0];
-        if (L->camlr == 0) p[0] = fminf(p[0], 0.0f); /* patch.cpp:188-193 */
-        else p[0] = fmaxf(p[0], 0.0f);
+        /* std::min / std::max operand order (patch.cpp:188-193) */
+        if (L->camlr == 0) p[0] = (0.0f < p[0]) ? 0.0f : p[0];
+        else p[0] = (p[0] < 0.0f) ? 0.0f : p[0];
         ptx = refx + p[0];
       }
       {
@@ -319,6 +320,7 @@ int dis_patches_level(const dis_level* L, const dis_params* prm, const float* i0
 /* PatGridClass::AggregateFlowDense without the fwd/bwd merge (patchgrid.cpp:213-275,377-394).
  * Written as the per-pixel gather the GPU uses: covering patches visited in
  * ascending ip = px*noph+py, which is the order the reference's scatter adds them. */
+#define STD_MAX(a, b) (((a) < (b)) ? (b) : (a)) /* std::max operand order */
 void dis_densify(const dis_level* L, const dis_params* prm, const float* p, const float* pweight,
                  float* flow_out) {
   const int P = L->P, C = L->noc, n = C * P * P, nop = L->nop;
@@ -347,10 +349,10 @@ void dis_densify(const dis_level* L, const dis_params* prm, const float* p, cons
             pw = pweight + (size_t)ip * n + (ry * P + rx) + (C - 1) * inb;
           }
           if (C == 1)
-            absw = 1.0f / fmaxf(minerrval, pw[0]);
+            absw = 1.0f / STD_MAX(minerrval, pw[0]);
           else {
-            absw = fmaxf(minerrval, pw[0]);
-            for (c = 1; c < C; ++c) absw += fmaxf(minerrval, pw[c]);
+            absw = STD_MAX(minerrval, pw[0]);
+            for (c = 1; c < C; ++c) absw += STD_MAX(minerrval, pw[c]);
             absw = 1.0f / absw;
           }
           we += absw;

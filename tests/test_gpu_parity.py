@@ -1,0 +1,190 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through
+the C-ABI (of_dis_b200/lib/libofdis_b200.so); the oracle (C restatement, pinned
+bitwise to the reference build) is only the checker.  Integer/bit-exact bar:
+all float outputs must be BITWISE equal, which is stronger than the 1e-3
+max-abs bar north_star states for the final .flo."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from of_dis_b200 import params, preprocess, synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_bits(got, exp, name):
+    got, exp = np.asarray(got), np.asarray(exp)
+    assert got.shape == exp.shape, (name, got.shape, exp.shape)
+    if got.dtype.kind == "f":
+        bad = bits(got) != bits(exp)
+        # +0/-0 and NaN payloads count as different on purpose
+        if bad.any():
+            d = np.abs(got.astype(np.float64) - exp.astype(np.float64))
+            raise AssertionError("%s: %d of %d values differ bitwise, max-abs %.3e, first at %s" %
+                                 (name, int(bad.sum()), bad.size, float(np.nanmax(d)), np.argwhere(bad)[0]))
+    else:
+        assert np.array_equal(got, exp), name
+
+
+@pytest.fixture(scope="module")
+def api():
+    from of_dis_b200 import api as _api
+
+    _api.lib()
+    return _api
+
+
+def _golden(path):
+    z = np.load(path)
+    prm = params.from_cli_numbers(z["cli"], noc=int(z["noc"]), nop=int(z["nop"]))
+    pyr = preprocess.PairPyramids(z["img0"], z["img1"], prm.sc_f, prm.p_samp_s)
+    return z, prm, pyr
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_fixtures_whole_run_and_patch_stage(path, api):
+    """Committed outputs of the reference build (tests/golden/make_golden.py)."""
+    z, prm, pyr = _golden(path)
+    ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    ctx.upload_pyramids(0, pyr)
+    ctx.run(1)
+    assert_bits(ctx.get_flow(0, prm.sc_l), z["flow"], "flow")
+    # patch stage of the finest level from a prescribed coarser flow
+    lv = prm.sc_l
+    ctx.set_flow(0, lv + 1, z["flow_prev"])
+    ctx.patgrid_optimize(lv, 0, 1, True)
+    ctx.patgrid_aggregate(lv, 0, 1)
+    got = ctx.get_patches(0, lv)
+    assert_bits(got["p"], z["p"], "p")
+    assert_bits(got["conv"], z["conv"], "conv")
+    assert_bits(got["cnt"], z["cnt"], "cnt")
+    assert_bits(ctx.get_flow(0, lv), z["dense"], "dense")
+    ctx.close()
+
+
+CASES = {
+    # name: (h, w, ch, params, amp, stereo)
+    "cfg2_1024x436_gray_op2": (436, 1024, 1, lambda: params.operating_point(2, 1024), 6.0, False),
+    "cfg1_640x480_gray_op2": (480, 640, 1, lambda: params.operating_point(2, 640), 6.0, False),
+    "gray_op2_motion40": (436, 1024, 1, lambda: params.operating_point(2, 1024), 40.0, False),
+    "gray_op1_no_tv": (436, 1024, 1, lambda: params.operating_point(1, 1024), 6.0, False),
+    "rgb_op3_l1cost_small": (270, 480, 3, lambda: params.from_cli_numbers(
+        "4 1 16 16 0.05 0.95 0 12 0.75 0 1 1 1 10 10 5 1 3 1.6 0".split(), noc=3), 6.0, False),
+    "stereo_op4_small": (250, 360, 1, lambda: params.from_cli_numbers(
+        "3 1 32 32 0.05 0.95 0 12 0.75 0 1 0 1 10 10 5 1 3 1.6 0".split(), noc=1, nop=1), 6.0, True),
+    "gray_p6_nopatnorm_sor5": (200, 320, 1, lambda: params.from_cli_numbers(
+        "3 1 8 8 0.05 0.95 0 6 0.5 0 0 0 1 10 10 5 2 5 1.5 0".split()), 6.0, False),
+    "gray_early_exit": (200, 320, 1, lambda: params.from_cli_numbers(
+        "3 1 16 2 0.05 0.95 0.5 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split()), 6.0, False),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_stages_and_whole_run_vs_oracle(name, api, oracle_port):
+    h, w, ch, mk, amp, stereo = CASES[name]
+    prm = mk()
+    i0, i1, _ = synth.synthetic_pair(h, w, ch, seed=1, amp=amp, stereo=stereo)
+    pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
+    ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    ctx.upload_pyramids(0, pyr)
+    lv = prm.sc_l
+    hh, ww = pyr.level_shape(lv + 1)
+    rng = np.random.default_rng(2)
+    fp = (rng.standard_normal((hh, ww, prm.nop)) * 2).astype(np.float32)
+    if stereo:
+        fp = -np.abs(fp)
+    # --- patch stage (K1-K4)
+    exp = oracle_port.port_level_patches(pyr, prm, lv, fp)
+    ctx.set_flow(0, lv + 1, fp)
+    ctx.patgrid_optimize(lv, 0, 1, True)
+    ctx.patgrid_aggregate(lv, 0, 1)
+    got = ctx.get_patches(0, lv)
+    for k in ("p", "pweight", "conv", "cnt"):
+        assert_bits(got[k], exp[k], "patch." + k)
+    dense = ctx.get_flow(0, lv)
+    assert_bits(dense, exp["dense"], "dense")
+    # --- refinement (K5-K12), stage by stage then end to end
+    if prm.usetvref:
+        st = oracle_port.varref_stages(pyr, prm, lv, dense, n_iters=2)
+        ctx.varref_refine(lv, 0, 1, n_inner=2)
+        for k in ("Ix", "Iy", "Iz", "Ixx", "Ixy", "Iyy", "Ixz", "Iyz"):
+            assert_bits(ctx.debug_get(k, 0, lv), st[k], "deriv." + k)
+        assert_bits(ctx.debug_get("mask", 0, lv)[0], st["mask"], "mask")
+        rec = ctx.debug_get("rec", 0, lv)
+        it = st["iters"][1]
+        if prm.nop == 2:
+            for idx, key in enumerate(("a11_inv", "a12_inv", "a22_inv", "b1", "b2", "sh", "sv")):
+                assert_bits(rec[..., idx], it[key], "rec." + key)
+        else:
+            assert_bits(rec[..., 1], it["b1"], "rec.b1")
+            assert_bits(rec[..., 2], it["sh"], "rec.sh")
+            assert_bits(rec[..., 3], it["sv"], "rec.sv")
+        dudv = ctx.debug_get("dudv", 0, lv)
+        assert_bits(dudv[..., 0], it["du"], "du")
+        if prm.nop == 2:
+            assert_bits(dudv[..., 1], it["dv"], "dv")
+        ctx.set_flow(0, lv, dense)
+        ctx.varref_refine(lv, 0, 1)
+        assert_bits(ctx.get_flow(0, lv), oracle_port.port_level_varref(pyr, prm, lv, dense), "varref")
+    # --- whole run
+    ctx.run(1)
+    assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "run")
+    ctx.close()
+
+
+def test_batch_of_frames_and_graph_replay(api, oracle_port):
+    """cfg 4 in miniature: 8 distinct pairs in one launch == 8 single runs; graph replay == eager."""
+    prm = params.operating_point(2, 1024)
+    nfr = 8
+    pyrs = []
+    for s in range(nfr):
+        i0, i1, _ = synth.synthetic_pair(436, 1024, 1, seed=100 + s)
+        pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
+    ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, nfr)
+    packed = np.stack([ctx.pack_frame(p) for p in pyrs])
+    ctx.upload_packed(0, nfr, packed)
+    ctx.run(nfr)
+    eager = [ctx.get_flow(f, prm.sc_l) for f in range(nfr)]
+    for f in (0, 3, 7):
+        assert_bits(eager[f], oracle_port.port_run(pyrs[f], prm), "frame %d" % f)
+    before = ctx.launch_count
+    ctx.set_graph_mode(True)
+    ctx.run(nfr)
+    ctx.run(nfr)
+    for f in range(nfr):
+        assert_bits(ctx.get_flow(f, prm.sc_l), eager[f], "graph frame %d" % f)
+    assert ctx.launch_count > before
+    ctx.close()
+
+
+def test_properties_at_full_size(api):
+    """Size-independent properties at BASELINE cfg 2 size: identical images -> exactly zero flow;
+    the reference-shaped OFClass wrapper gives the same result as the batch engine."""
+    prm = params.operating_point(2, 1024)
+    i0, i1, gt = synth.synthetic_pair(436, 1024, 1, seed=5)
+    pyr = preprocess.PairPyramids(i0, i0, prm.sc_f, prm.p_samp_s)
+    ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    ctx.upload_pyramids(0, pyr)
+    ctx.run(1)
+    assert np.abs(ctx.get_flow(0, prm.sc_l)).max() == 0.0
+    pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
+    ctx.upload_pyramids(0, pyr)
+    ctx.run(1)
+    a = ctx.get_flow(0, prm.sc_l)
+    ctx.close()
+    out = np.zeros_like(a)
+    api.OFClass(pyr.i0, pyr.i0x, pyr.i0y, pyr.i1, pyr.i1x, pyr.i1y, pyr.imgpadding, out, None, pyr.width, pyr.height,
+                prm.sc_f, prm.sc_l, prm.max_iter, prm.min_iter, prm.dp_thresh, prm.dr_thresh, prm.res_thresh,
+                prm.p_samp_s, prm.patove, prm.usefbcon, prm.costfct, prm.noc, prm.patnorm, prm.usetvref, prm.tv_alpha,
+                prm.tv_gamma, prm.tv_delta, prm.tv_innerit, prm.tv_solverit, prm.tv_sor, 0)
+    assert_bits(out, a, "OFClass wrapper")
+    full = preprocess.postprocess(a, prm.sc_l, pyr.padw, pyr.padh, pyr.width_org, pyr.height_org)
+    epe = np.sqrt(((full - gt) ** 2).sum(-1)).mean()
+    assert epe < 0.5, epe
