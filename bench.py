@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- Mpix/s of dense DIS flow on synthetic 1024x436 pairs (op-point 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+A "step" is one pass of the hot path (all pyramid levels: patch inverse search,
+densification, variational refinement == the reference's "O.Flow Run-Time"
+region, oflow.cpp:113-114,355-360) over B pairs per GPU.  Pixels are counted at
+the ORIGINAL image size, once per pair.
+
+  value : device-timed, padded pyramids already resident in HBM
+  e2e   : same metric through the C-ABI with pinned HOST buffers; H2D of the
+          packed pyramids and D2H of the flows inside the timed region
+  roofline     : dominant kernel (lexicographic SOR), algorithmic bytes / CUDA-event time
+  cpu_baseline : the reference CPU build (oracle/_ref) or the C port on this box's cores
+
+Under torchrun every rank owns B pairs (weak scaling, no data-path collective;
+frames are independent -- DESIGN.md section 6); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+H_ORG, W_ORG = 436, 1024
+OP_POINT = 2
+
+
+def make_pairs(n, seed0):
+    from of_dis_b200 import params, preprocess, synth
+
+    prm = params.operating_point(OP_POINT, W_ORG)
+    pyrs = []
+    for s in range(n):
+        i0, i1, _ = synth.synthetic_pair(H_ORG, W_ORG, 1, seed=seed0 + s)
+        pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
+    return prm, pyrs
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                if t0 - 0.05 <= ts <= t1 + 0.2:
+                    sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_mpix(prm, pyrs, seconds, threads):
+    """Frame-parallel reference CPU build: `threads` workers, each running whole pairs
+    (OFClass instances share no mutable state).  Returns (Mpix/s, kind, n_pairs)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import port_driver, ref_driver
+
+    if ref_driver.ref_available(prm.flavour()):
+        kind, fn = "reference", ref_driver.ref_run
+    else:
+        kind, fn = "port", port_driver.port_run
+        port_driver.build()
+    fn(pyrs[0], prm)  # warm
+    done = 0
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        while time.perf_counter() - t0 < seconds:
+            list(ex.map(lambda p: fn(p, prm), pyrs))
+            done += len(pyrs)
+    dt = time.perf_counter() - t0
+    return done * H_ORG * W_ORG / dt / 1e6, kind, done
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    npairs = args.batch * world
+    threads = min(cores, npairs)
+    prm, pyrs = make_pairs(npairs, 0)
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import port_driver, ref_driver
+
+    if ref_driver.ref_available(prm.flavour()):
+        kind, fn = "reference", ref_driver.ref_run
+    else:
+        kind, fn = "port", port_driver.port_run
+        port_driver.build()
+    times = []
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            list(ex.map(lambda p: fn(p, prm), pyrs))
+            if s >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    val = npairs * H_ORG * W_ORG / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": "Mpix/s dense flow (1024x436, op-point 2)", "value": val, "unit": "Mpix/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": threads, "kind": kind,
+                         "sample": "%d pairs per step, frame-parallel over %d threads (host has %d cores), "
+                                   "timer = OFClass ctor region" % (npairs, threads, cores)},
+        "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": "%d x (1024x436 gray pair, op-point 2: P=8 ov=0.4 levels 5..3, 12 GN iters, TV 3 SOR sweeps) "
+                        "per GPU = BASELINE configs[3] shard on configs[1] geometry" % args.batch,
+            "pairs_per_gpu": args.batch, "pairs_total": args.batch * world, "parallelism": "frames x%d" % world,
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from of_dis_b200 import api
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    prm, pyrs = make_pairs(B, 1000 * rank)
+    stream = torch.cuda.current_stream()
+    ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, B, device=local,
+                      stream=stream.cuda_stream)
+    ff = ctx.packed_frame_floats
+    host_in = torch.empty((B, ff), dtype=torch.float32).pin_memory()
+    for f, p in enumerate(pyrs):
+        ctx.pack_frame(p, host_in[f].numpy())
+    li = ctx.level_info(prm.sc_l)
+    flow_floats = li["w"] * li["h"] * prm.nop
+    host_out = torch.empty((B, flow_floats), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1.0)  # L2 flush, outside the timed interval
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            step_fn()
+            b.record(stream)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / steps  # ms per step
+
+    def maxrank(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput -----------------------------------------
+    ctx.upload_packed(0, B, host_in.data_ptr())
+    ctx.set_graph_mode(True)
+    resident = lambda: ctx.run(B)  # noqa: E731
+    for _ in range(args.warmup):
+        resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    l0 = ctx.launch_count
+    t0 = time.time()
+    ms_res = timed(resident, args.steps)
+    launches = (ctx.launch_count - l0) // args.steps
+    barrier()
+    ms_res = maxrank(ms_res)
+
+    # ---- end to end with host buffers -----------------------------------------
+    def e2e():
+        ctx.upload_packed(0, B, host_in.data_ptr())
+        ctx.run(B)
+        ctx.get_flow_batch(0, B, host_out.data_ptr())
+
+    for _ in range(args.warmup):
+        e2e()
+    barrier()
+    w0 = time.perf_counter()
+    ms_e2e = timed(e2e, args.steps)
+    wall_e2e = (time.perf_counter() - w0) / args.steps * 1e3
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    ms_e2e = maxrank(ms_e2e)
+
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pix = B * world * H_ORG * W_ORG
+    value = pix / (ms_res * 1e-3) / 1e6
+    e2e_val = pix / (ms_e2e * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (SOR), measured live with CUDA events ----
+    ctx.set_graph_mode(False)
+    roof = None
+    try:
+        prof = ctx.profile_kernels(B, steps=max(3, min(args.steps, 10)))
+        peak, how = peaks()
+        sor = prof["sor"]
+        alg = 0
+        for lv in range(prm.sc_l, prm.sc_f + 1):
+            g = ctx.level_info(lv)
+            alg += prm.tv_innerit * (lv + 1) * 44 * g["w"] * g["h"] * B  # bytes, SURVEY 8(d)
+        ach = alg / (sor["ms_per_step"] * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("sor_dram_bytes_per_launch")
+        roof = {"bound": "hbm", "kernel": "sor_kernel (lexicographic SOR, all sweeps fused)", "achieved": ach,
+                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": how,
+                "algorithmic_bytes_per_step": alg, "kernel_ms_per_step": sor["ms_per_step"],
+                "launches_per_step": sor["launches_per_step"],
+                "share_of_step": {k: v["ms_per_step"] for k, v in prof.items()}}
+    except Exception as e:  # profiling hook missing must not lose the headline numbers
+        roof = {"bound": "hbm", "achieved": None, "peak": peaks()[0], "unit": "GB/s", "frac": None, "traffic": None,
+                "error": str(e)}
+
+    cores = os.cpu_count() or 1
+    threads = min(cores, B)
+    cpu_val, kind, done = cpu_reference_mpix(prm, pyrs, args.cpu_seconds, threads) if world == 1 else (None, None, 0)
+    line = {
+        "metric": "Mpix/s dense flow (1024x436, op-point 2)", "value": value, "unit": "Mpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
+                "h2d_bytes_per_step": int(B * ff * 4), "d2h_bytes_per_step": int(B * flow_floats * 4)},
+        "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
+        "clocks": clocks, "roofline": roof,
+    }
+    if cpu_val is not None:
+        line["cpu_baseline"] = {"value": cpu_val, "unit": "Mpix/s", "cores": threads, "kind": kind,
+                                "sample": "%d pairs of the same workload, frame-parallel over %d threads for %.0f s "
+                                          "(host has %d cores)" % (done, threads, args.cpu_seconds, cores)}
+    print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -129,6 +129,10 @@ int ofdis_debug_varref_iters(ofdis_ctx* ctx, int level, int f0, int f1, int n_in
 
 /* Number of kernels this library has launched on the context since creation. */
 long ofdis_launch_count(const ofdis_ctx* ctx);
+/* Eager ofdis_run x steps with a CUDA-event pair around every launch group; sums per class
+ * {0 patch, 1 densify, 2 refinement setup (warp+derivatives), 3 assemble, 4 SOR} into
+ * ms_by_class[5] / launches_by_class[5] (launch groups, one per stage call). */
+int ofdis_profile_run(ofdis_ctx* ctx, int nframes, int steps, double* ms_by_class, long* launches_by_class);
 /* CUDA-graph replay of ofdis_run (captured on first use per nframes). */
 int ofdis_set_graph_mode(ofdis_ctx* ctx, int enabled);
 

@@ -27,7 +27,7 @@ EXPORTS = [
     "ofdis_upload_level", "ofdis_packed_frame_floats", "ofdis_packed_offset", "ofdis_upload_packed",
     "ofdis_patgrid_optimize", "ofdis_patgrid_aggregate", "ofdis_varref_refine", "ofdis_run", "ofdis_sync",
     "ofdis_get_flow", "ofdis_set_flow", "ofdis_get_flow_batch", "ofdis_get_patches", "ofdis_debug_get",
-    "ofdis_debug_varref_iters", "ofdis_launch_count", "ofdis_set_graph_mode",
+    "ofdis_debug_varref_iters", "ofdis_launch_count", "ofdis_set_graph_mode", "ofdis_profile_run",
 ]
 
 
@@ -74,6 +74,7 @@ def lib():
         L.ofdis_get_patches.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4
         L.ofdis_debug_get.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
         L.ofdis_set_graph_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.ofdis_profile_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -201,6 +202,14 @@ class Context:
 
     def set_graph_mode(self, on: bool):
         self._ck(lib().ofdis_set_graph_mode(self._h, 1 if on else 0))
+
+    def profile_kernels(self, nframes: int, steps: int = 5):
+        """Eager runs with CUDA events around each stage: {class: ms_per_step, launches_per_step}."""
+        ms = (ctypes.c_double * 5)()
+        n = (ctypes.c_long * 5)()
+        self._ck(lib().ofdis_profile_run(self._h, nframes, steps, ms, n))
+        names = ("patch", "densify", "vr_setup", "assemble", "sor")
+        return {k: {"ms_per_step": ms[i] / steps, "launches_per_step": n[i] / steps} for i, k in enumerate(names)}
 
     @property
     def launch_count(self) -> int:

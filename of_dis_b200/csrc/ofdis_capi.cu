@@ -34,6 +34,7 @@ struct ofdis_ctx {
   long launches = 0;
   int last_vr_level = -1, last_vr_f0 = 0;
   bool graph_mode = false;
+  Profiler* prof = nullptr;         // non-null only inside ofdis_profile_run
   std::map<long, cudaGraphExec_t> graphs;
   std::map<long, long> graph_launches;
   std::string err;
@@ -297,7 +298,7 @@ int ofdis_patgrid_optimize(ofdis_ctx* ctx, int level, int f0, int f1, int init_f
   if (!ctx) return OFDIS_ERR_ARG;
   LevelGeom* L = level_of(ctx, level);
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_optimize: bad argument");
-  const int n = launch_patch_optimize(*L, ctx->pp, f0, f1, init_from_coarser != 0, ctx->stream);
+  const int n = launch_patch_optimize(*L, ctx->pp, f0, f1, init_from_coarser != 0, ctx->stream, ctx->prof);
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "patch_optimize_kernel launch", cudaGetLastError());
   ctx->launches += n;
   return OFDIS_OK;
@@ -307,7 +308,7 @@ int ofdis_patgrid_aggregate(ofdis_ctx* ctx, int level, int f0, int f1) {
   if (!ctx) return OFDIS_ERR_ARG;
   LevelGeom* L = level_of(ctx, level);
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_aggregate: bad argument");
-  const int n = launch_densify(*L, f0, f1, ctx->stream);
+  const int n = launch_densify(*L, f0, f1, ctx->stream, ctx->prof);
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "densify_kernel launch", cudaGetLastError());
   ctx->launches += n;
   return OFDIS_OK;
@@ -328,7 +329,7 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   vp.half_delta_over3 = ctx->prm.tv_delta * 0.5f / 3.0f;
   VarRefPlanes pl = ctx->planes;
   pl.plane = (size_t)L->pitch * L->h;
-  const int n = launch_varref(*L, pl, vp, f0, f1, ctx->stream);
+  const int n = launch_varref(*L, pl, vp, f0, f1, ctx->stream, ctx->prof);
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "varref kernels launch", cudaGetLastError());
   ctx->launches += n;
   ctx->last_vr_level = level;
@@ -456,5 +457,34 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
 }
 
 long ofdis_launch_count(const ofdis_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ofdis_profile_run(ofdis_ctx* ctx, int nframes, int steps, double* ms_by_class, long* launches_by_class) {
+  if (!ctx || steps < 1 || !ms_by_class || !launches_by_class) return OFDIS_ERR_ARG;
+  if (nframes < 1 || nframes > ctx->max_frames) return fail(ctx, OFDIS_ERR_ARG, "profile_run: bad frame count");
+  CK(cudaSetDevice(ctx->device));
+  Profiler prof;
+  prof.st = ctx->stream;
+  ctx->prof = &prof;
+  int rc = OFDIS_OK;
+  for (int s = 0; s < steps && rc == OFDIS_OK; ++s) rc = run_levels(ctx, nframes, 0);
+  ctx->prof = nullptr;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  for (int k = 0; k < KC_COUNT; ++k) {
+    ms_by_class[k] = 0.0;
+    launches_by_class[k] = 0;
+  }
+  for (auto& r : prof.recs) {
+    float ms = 0.f;
+    if (e == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ms_by_class[r.cls] += ms;
+      launches_by_class[r.cls] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(ctx, OFDIS_ERR_CUDA, "profile_run sync", e);
+  return OFDIS_OK;
+}
 
 }  // extern "C"

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace ofdis {
 
 // Per-level geometry, mirrors camparam/optparam (oflow.h:16-76) + grid (patchgrid.cpp:42-48).
@@ -47,12 +49,38 @@ struct VarRefParams {
   int n_inner, n_solver;
 };
 
+// Optional per-kernel-class CUDA-event timing (bench.py roofline; eager mode only).
+enum KernelClass { KC_PATCH = 0, KC_DENSIFY, KC_VR_SETUP, KC_VR_ASSEMBLE, KC_VR_SOR, KC_COUNT };
+struct Profiler {
+  cudaStream_t st = nullptr;
+  struct Rec { int cls; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  cudaEvent_t cur = nullptr;
+  int cur_cls = -1;
+  void begin(int cls) {
+    cudaEventCreate(&cur);
+    cudaEventRecord(cur, st);
+    cur_cls = cls;
+  }
+  void end() {
+    cudaEvent_t b;
+    cudaEventCreate(&b);
+    cudaEventRecord(b, st);
+    recs.push_back({cur_cls, cur, b});
+  }
+};
+struct ProfScope {
+  Profiler* p;
+  ProfScope(Profiler* prof, int cls) : p(prof) { if (p) p->begin(cls); }
+  ~ProfScope() { if (p) p->end(); }
+};
+
 // launchers (each returns the number of kernels launched, <0 on error)
 int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int f1, bool init_from_coarser,
-                          cudaStream_t st);
-int launch_densify(const LevelGeom& g, int f0, int f1, cudaStream_t st);
+                          cudaStream_t st, Profiler* prof = nullptr);
+int launch_densify(const LevelGeom& g, int f0, int f1, cudaStream_t st, Profiler* prof = nullptr);
 int launch_varref(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
-                  cudaStream_t st);
+                  cudaStream_t st, Profiler* prof = nullptr);
 
 // ---- exact-arithmetic helpers -------------------------------------------------
 // std::min/std::max semantics of the reference (operand order matters for +-0/NaN)

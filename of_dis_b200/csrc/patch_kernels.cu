@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(256) densify_kernel(LevelGeom g, int f0) {
 }  // namespace
 
 int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int f1, bool init_from_coarser,
-                          cudaStream_t st) {
+                          cudaStream_t st, Profiler* prof) {
+  ProfScope scope(prof, KC_PATCH);
   const int n = g.novals;
   const int NK = (n / 8) + (((n % 8) >= 4) ? 1 : 0);
   int threads = 256;
@@ -365,7 +366,8 @@ int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_densify(const LevelGeom& g, int f0, int f1, cudaStream_t st) {
+int launch_densify(const LevelGeom& g, int f0, int f1, cudaStream_t st, Profiler* prof) {
+  ProfScope scope(prof, KC_DENSIFY);
   const dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8, f1 - f0);
   if (g.nop == 2) densify_kernel<2><<<grid, block, 0, st>>>(g, f0);
   else densify_kernel<1><<<grid, block, 0, st>>>(g, f0);

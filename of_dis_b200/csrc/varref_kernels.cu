@@ -503,15 +503,18 @@ __global__ void __launch_bounds__(PF > 2 ? 512 : 1024)
 
 template <int C, int NOP>
 static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
-                           cudaStream_t st) {
+                           cudaStream_t st, Profiler* prof) {
   int launches = 0;
   const int nf = f1 - f0;
   const dim3 block(TX, TY), grid((g.w + TX - 1) / TX, (g.h + TY - 1) / TY, nf);
   const dim3 gridc(grid.x, grid.y, nf * C);
-  warp_kernel<C, NOP><<<grid, block, 0, st>>>(g, pl, f0);
-  deriv1_kernel<C><<<gridc, block, 0, st>>>(g, pl);
-  deriv2_kernel<C><<<gridc, block, 0, st>>>(g, pl);
-  cudaMemsetAsync(pl.dudv, 0, sizeof(float2) * pl.plane * nf, st);
+  {
+    ProfScope scope(prof, KC_VR_SETUP);
+    warp_kernel<C, NOP><<<grid, block, 0, st>>>(g, pl, f0);
+    deriv1_kernel<C><<<gridc, block, 0, st>>>(g, pl);
+    deriv2_kernel<C><<<gridc, block, 0, st>>>(g, pl);
+    cudaMemsetAsync(pl.dudv, 0, sizeof(float2) * pl.plane * nf, st);
+  }
   launches += 3;
   // sweeps per SOR launch: all of them when (sweeps x rows) fits one CTA
   const int K = vp.n_solver;
@@ -525,12 +528,16 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
     else cudaFuncSetAttribute(sor_kernel<NOP, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   for (int it = 0; it < vp.n_inner; ++it) {
-    assemble_kernel<C, NOP><<<grid, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
+    {
+      ProfScope scope(prof, KC_VR_ASSEMBLE);
+      assemble_kernel<C, NOP><<<grid, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
+    }
     ++launches;
     const int last = (it == vp.n_inner - 1) ? 1 : 0;
     const int nl = fused ? 1 : K;
     for (int s = 0; s < nl; ++s) {
       const int wf = (last && s == nl - 1) ? 1 : 0;
+      ProfScope scope(prof, KC_VR_SOR);
       if (big) sor_kernel<NOP, 2><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, wf);
       else sor_kernel<NOP, 8><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, wf);
       ++launches;
@@ -540,11 +547,11 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
 }
 
 int launch_varref(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
-                  cudaStream_t st) {
-  if (g.noc == 1 && g.nop == 2) return launch_varref_t<1, 2>(g, pl, vp, f0, f1, st);
-  if (g.noc == 3 && g.nop == 2) return launch_varref_t<3, 2>(g, pl, vp, f0, f1, st);
-  if (g.noc == 1 && g.nop == 1) return launch_varref_t<1, 1>(g, pl, vp, f0, f1, st);
-  if (g.noc == 3 && g.nop == 1) return launch_varref_t<3, 1>(g, pl, vp, f0, f1, st);
+                  cudaStream_t st, Profiler* prof) {
+  if (g.noc == 1 && g.nop == 2) return launch_varref_t<1, 2>(g, pl, vp, f0, f1, st, prof);
+  if (g.noc == 3 && g.nop == 2) return launch_varref_t<3, 2>(g, pl, vp, f0, f1, st, prof);
+  if (g.noc == 1 && g.nop == 1) return launch_varref_t<1, 1>(g, pl, vp, f0, f1, st, prof);
+  if (g.noc == 3 && g.nop == 1) return launch_varref_t<3, 1>(g, pl, vp, f0, f1, st, prof);
   return -1;
 }
 
