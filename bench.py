@@ -202,7 +202,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     prm, pyrs = make_pairs(B, 1000 * rank)
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: the context enqueues on it and torch.cuda.Event times it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, B, device=local,
                       stream=stream.cuda_stream)
     ff = ctx.packed_frame_floats

@@ -212,13 +212,15 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
     const LevelGeom& Lf = ctx->lev[0];
     const size_t plane = (size_t)Lf.pitch * Lf.h;
     const int C = prm->noc;
-    const size_t per_frame = plane * (1 + C + 8 * C + 2 + 8);
+    // skewed SOR arrays: (W4 + h) diagonals x hpad rows, 8 (rec) + 2 (dudv) float4 per block
+    const size_t diag = (size_t)((Lf.w + 3) / 4 + Lf.h) * (((Lf.h + 31) / 32) * 32);
+    const size_t per_frame = plane * (1 + C + 8 * C) + diag * 4 * (8 + 2);
     ok = dalloc((void**)&ctx->d_planes, sizeof(float) * per_frame * max_frames);
     if (ok) {
       float* q = ctx->d_planes;
       VarRefPlanes& P = ctx->planes;
-      P.rec = reinterpret_cast<float4*>(q); q += plane * 8 * max_frames;   // 32-byte records first (alignment)
-      P.dudv = reinterpret_cast<float2*>(q); q += plane * 2 * max_frames;
+      P.rec = reinterpret_cast<float4*>(q); q += diag * 4 * 8 * max_frames;   // records first (alignment)
+      P.dudv = reinterpret_cast<float4*>(q); q += diag * 4 * 2 * max_frames;
       P.mask = q; q += plane * max_frames;
       P.avg = q; q += plane * C * max_frames;
       for (int k = 0; k < 8; ++k) { P.deriv[k] = q; q += plane * C * max_frames; }
@@ -329,6 +331,12 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   vp.half_delta_over3 = ctx->prm.tv_delta * 0.5f / 3.0f;
   VarRefPlanes pl = ctx->planes;
   pl.plane = (size_t)L->pitch * L->h;
+  pl.hpad = ((L->h + 31) / 32) * 32;
+  {
+    const size_t diag = (size_t)((L->w + 3) / 4 + L->h) * pl.hpad;
+    pl.rec_stride = diag * (L->nop == 2 ? 8 : 4);
+    pl.dudv_stride = diag * 2;
+  }
   const int n = launch_varref(*L, pl, vp, f0, f1, ctx->stream, ctx->prof);
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "varref kernels launch", cudaGetLastError());
   ctx->launches += n;
@@ -444,11 +452,27 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
       n = plane * C;
     }
   if (!strcmp(name, "mask")) { src = ctx->planes.mask + (size_t)fr * plane; n = plane; }
-  if (!strcmp(name, "dudv")) { src = reinterpret_cast<const float*>(ctx->planes.dudv + (size_t)fr * plane); n = plane * 2; }
-  if (!strcmp(name, "rec")) {
-    const int rf = (L->nop == 2) ? 8 : 4;
-    src = reinterpret_cast<const float*>(ctx->planes.rec) + (size_t)fr * plane * rf;
-    n = plane * rf;
+  if (!strcmp(name, "dudv") || !strcmp(name, "rec")) {
+    // stored skewed (see VarRefPlanes); returned in natural (h, pitch, per-pixel) order
+    const bool is_rec = name[0] == 'r';
+    const int hpad = ((L->h + 31) / 32) * 32, W4 = (L->w + 3) / 4;
+    const int nq = is_rec ? (L->nop == 2 ? 8 : 4) : 2;            // float4 per 4-pixel block
+    const int per = is_rec ? (L->nop == 2 ? 8 : 4) : 2;           // floats per pixel
+    const size_t stride = (size_t)(W4 + L->h) * hpad * nq;        // float4 per frame
+    if (plane * per > max_floats) return OFDIS_ERR_ARG;
+    std::vector<float> raw(stride * 4);
+    const float4* base = (is_rec ? ctx->planes.rec : ctx->planes.dudv) + (size_t)fr * stride;
+    if (cudaMemcpyAsync(raw.data(), base, sizeof(float) * raw.size(), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return OFDIS_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return OFDIS_ERR_CUDA;
+    for (int j = 0; j < L->h; ++j)
+      for (int i = 0; i < L->w; ++i)
+        for (int e = 0; e < per; ++e) {
+          // rec: pixel c owns floats c*per..; dudv: float4 0 = du x4, float4 1 = dv x4
+          const int fl = is_rec ? (i & 3) * per + e : e * 4 + (i & 3);
+          const size_t f4 = skew_f4(i >> 2, j, fl / 4, nq, hpad);
+          dst[((size_t)j * L->pitch + i) * per + e] = raw[f4 * 4 + (fl & 3)];
+        }
+    return (long)(plane * per);
   }
   if (!src || n > max_floats) return OFDIS_ERR_ARG;
   if (cudaMemcpyAsync(dst, src, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return OFDIS_ERR_CUDA;

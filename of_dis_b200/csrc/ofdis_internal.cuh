@@ -39,10 +39,22 @@ struct VarRefPlanes {
   float* mask;             // [frames]
   float* avg;              // [frames][C]   0.5*(I1w+I0)            (setup only)
   float* deriv[8];         // Ix Iy Iz Ixx Ixy Iyy Ixz Iyz, each [frames][C]
-  float2* dudv;            // [frames] interleaved (du,dv); stereo uses .x
-  float4* rec;             // [frames] SOR records, 2 x float4 per pixel (flow) / 1 (stereo)
-  size_t plane;            // pitch*h
+  // Skewed ("anti-diagonal major") storage shared by assemble_kernel and sor_kernel: the 4-pixel
+  // block (row j, columns 4I..4I+3) lives at [d = I + j][q][j] with q the float4 inside the block,
+  // so that the lanes of a SOR warp (consecutive rows, same d at a given super-step) touch
+  // consecutive 16-byte words.  See skew_f4() below.
+  float4* dudv;            // [frames][(W4+h)][2][hpad] float4 = (du,dv) x 2 pixels
+  float4* rec;             // [frames][(W4+h)][4*RF][hpad] float4, RF = 2 (flow) / 1 (stereo)
+  size_t plane;            // pitch*h (natural planes)
+  size_t dudv_stride;      // float4 per frame
+  size_t rec_stride;       // float4 per frame
+  int hpad;                // rows padded to a multiple of 32
 };
+
+// float4 index of float4 q of block (I, j) in a skewed array with NQ float4 per block
+__host__ __device__ __forceinline__ size_t skew_f4(int I, int j, int q, int NQ, int hpad) {
+  return ((size_t)(I + j) * NQ + q) * hpad + j;
+}
 
 struct VarRefParams {
   float quarter_alpha, half_gamma_over3, half_delta_over3, omega;

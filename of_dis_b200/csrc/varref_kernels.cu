@@ -133,7 +133,13 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   const int tid = threadIdx.y * TX + threadIdx.x;
   const int w = g.w, h = g.h, pitch = g.pitch;
   const float* flow = g.flow + (size_t)frame * g.flow_frame_stride;
-  const float2* dudv = pl.dudv + (size_t)fr * pl.plane;
+  const float* dudv = reinterpret_cast<const float*>(pl.dudv + (size_t)fr * pl.dudv_stride);
+  const int hpad = pl.hpad;
+  // (du,dv) of pixel (x,y) in the skewed layout: float4 0 of a block holds du x4, float4 1 dv x4
+  auto dudv_at = [&](int x, int y) -> float2 {
+    const size_t b = skew_f4(x >> 2, y, 0, 2, hpad) * 4 + (x & 3);
+    return make_float2(dudv[b], (NOP == 2) ? dudv[b + 4 * hpad] : 0.0f);
+  };
 
   // uu = wx + du (vv likewise); first iteration: uu = wx (refine_variational.cpp:189-190).
   // Coordinates are clamped, which also realises the replicate border of the 3-tap
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     uv.x = f[0];
     uv.y = (NOP == 2) ? f[1] : 0.0f;
     if (!first) {
-      const float2 d = dudv[gy * pitch + gx];
+      const float2 d = dudv_at(gx, gy);
       if (NOP == 2) {
         uv.x = uv.x + d.x;
         uv.y = uv.y + d.y;
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
 
   const int o = j * pitch + i;
   const float m = pl.mask[(size_t)fr * pl.plane + o];
-  const float2 d = dudv[o];
+  const float2 d = dudv_at(i, j);
   const float u = d.x, v = (NOP == 2) ? d.y : 0.0f;
   const float hdo3 = vp.half_delta_over3, hgo3 = vp.half_gamma_over3;
   float A11 = 0.f, A12 = 0.f, A22 = 0.f, B1 = 0.f, B2 = 0.f;
@@ -316,9 +322,9 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     else dps = hl + hh + vt + vv;
     const float iA11 = A22 + dps, iA22 = A11 + dps;
     const float det = iA11 * iA22 - A12 * A12;
-    float4* rec = pl.rec + ((size_t)fr * pl.plane + o) * 2;
-    rec[0] = make_float4(iA11 / det, A12 / -det, iA22 / det, B1);
-    rec[1] = make_float4(B2, hh, vv, 0.0f);
+    float4* rec = pl.rec + (size_t)fr * pl.rec_stride;
+    rec[skew_f4(i >> 2, j, (i & 3) * 2, 8, hpad)] = make_float4(iA11 / det, A12 / -det, iA22 / det, B1);
+    rec[skew_f4(i >> 2, j, (i & 3) * 2 + 1, 8, hpad)] = make_float4(B2, hh, vv, 0.0f);
   } else {
     // sor_coupled_slow_but_readable_DE (solver.c:438-460): A11 = a11 + sum_dpsis (top,left,bottom,right)
     float sum = 0.0f;
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     if (i > 0) sum += hl;
     if (j < h - 1) sum += vv;
     if (i < w - 1) sum += hh;
-    pl.rec[(size_t)fr * pl.plane + o] = make_float4(A11 + sum, B1, hh, vv);
+    pl.rec[(size_t)fr * pl.rec_stride + skew_f4(i >> 2, j, i & 3, 4, hpad)] = make_float4(A11 + sum, B1, hh, vv);
   }
 }
 
@@ -335,167 +341,237 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
 //
 // sor_coupled (solver.c:77-421) visits pixels in raster order; pixel (i,j) of
 // sweep k reads left/top of sweep k and right/bottom (and itself) of sweep k-1.
-// With the schedule  t = i + j + 2k  every value is produced exactly one step
-// before its consumers need it, so thread (k,j) walks row j one pixel per step
-// and exchanges (du,dv,sv) with its neighbours through a double-buffered
-// shared-memory board; one __syncthreads per step.  The arithmetic per pixel is
-// the reference's expression, hence bit-identical.  Sweep 0 takes the previous
-// values from global memory (prefetched PF steps ahead), the last sweep writes
-// the result (and, on the last inner iteration, flow = w + dw; K12).
-template <int NOP, int PF>
-__global__ void __launch_bounds__(PF > 2 ? 512 : 1024)
-    sor_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int f0, int K, int write_flow) {
-  extern __shared__ float4 s_pub[];  // [2][K][h+2]
+// Rows are cut into blocks of 4 columns.  With the schedule
+//      T = I + j + 2k          (I = column block, j = row, k = sweep)
+// every value is produced exactly one super-step before its consumers need it:
+// thread (k,j) walks row j one block per super-step, keeps the left neighbour in
+// registers and exchanges (du,dv,sv) of its block with the threads (k,j+1),
+// (k+1,j) and (k+1,j-1) through a double-buffered shared-memory board; one
+// __syncthreads per super-step, W/4 + h + 2K super-steps in all.  Inside a block
+// the four pixels are updated sequentially with the reference's expression, so
+// the result is bit-identical to the raster scan.  Sweep 0 takes the previous
+// values from global memory (register-prefetched one super-step ahead), the last
+// sweep writes du,dv (and, on the last inner iteration, flow = w + dw; K12).
+// Row-class and border cases are selects, not branches: the loop body is
+// straight-line code.
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Thread layout: tid = k*hpad + j with hpad a multiple of 32, so the sweep index k (and with
+// it the "sweep 0 reads global / last sweep writes global" roles) is uniform per warp.
+// Out-of-range super-steps execute the same straight-line code on clamped addresses and
+// simply do not store to global memory; whatever they put on the board is never consumed
+// by an in-range neighbour (SOR schedule).
+template <int NOP, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+    sor_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int f0, int K, int hpad, int write_flow) {
+  extern __shared__ float4 s_pub[];  // [2][K][h+2][NF]
+  constexpr int NF = (NOP == 2) ? 3 : 2;   // float4 per board entry: du x4, (dv x4), sv x4
+  constexpr int RF = (NOP == 2) ? 2 : 1;   // float4 per pixel record
   const int fr = blockIdx.x, frame = f0 + fr;
   const int w = g.w, h = g.h, pitch = g.pitch;
   const int tid = threadIdx.x;
-  const bool valid = tid < K * h;
-  const int k = valid ? tid / h : 0, j = valid ? tid - k * h : 0;
+  const int k = tid / hpad, jraw = tid - k * hpad;
+  const bool valid = jraw < h;
+  const int j = valid ? jraw : h - 1;      // idle lanes shadow the last row, never store
   const int hb = h + 2;
-  float4* pub0 = s_pub;
-  float4* pub1 = s_pub + K * hb;
-  constexpr int RF = (NOP == 2) ? 2 : 1;
-  const float4* rec = pl.rec + ((size_t)fr * pl.plane + (size_t)j * pitch) * RF;
-  float2* drow = pl.dudv + (size_t)fr * pl.plane + (size_t)j * pitch;
+  const unsigned bufbytes = (unsigned)(K * hb * NF) * 16u;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_pub);
+  const unsigned a_me = sbase + (unsigned)((k * hb + j + 1) * NF) * 16u;
+  const unsigned a_top = sbase + (unsigned)((k * hb + j) * NF) * 16u;
+  const int km = k > 0 ? k - 1 : 0;
+  const unsigned a_right = sbase + (unsigned)((km * hb + j + 1) * NF) * 16u;
+  const unsigned a_bot = sbase + (unsigned)((km * hb + j + 2) * NF) * 16u;
+  const bool first_row = (j == 0), last_row = (j == h - 1);
+  const bool k0 = (k == 0), klast = (k == K - 1);
   const float omega = vp.omega;
-  float* flow = g.flow + (size_t)frame * g.flow_frame_stride + (size_t)j * w * NOP;
 
-  // prefetch ring: slot q holds column (t%PF==q) data
-  float4 ra[PF], rb[PF];
-  float2 rr[PF], rbt[PF];
-#pragma unroll
-  for (int q = 0; q < PF; ++q) {
-    ra[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    rb[q] = ra[q];
-    rr[q] = make_float2(0.f, 0.f);
-    rbt[q] = rr[q];
-  }
-  // warm-up: columns 0..PF-1 are needed at steps t0..t0+PF-1, t0 = j+2k
+  // skewed arrays: block (I, j) float4 q at ((I + j) * NQ + q) * hpad + j
+  constexpr int NQ = 4 * RF;
+  const int jb = last_row ? j : j + 1;  // bottom row (clamped; unused on the last row)
+  const float4* const recp = pl.rec + (size_t)fr * pl.rec_stride + (size_t)j * NQ * hpad + j;
+  float4* const drow4 = pl.dudv + (size_t)fr * pl.dudv_stride + (size_t)j * 2 * hpad + j;
+  const float4* const dbot4 = pl.dudv + (size_t)fr * pl.dudv_stride + (size_t)jb * 2 * hpad + jb;
+  const int bstep_r = NQ * hpad, bstep_d = 2 * hpad;  // float4 per block step
+  float* const flow = g.flow + (size_t)frame * g.flow_frame_stride + (size_t)j * w * NOP;
+
+  const int W4 = (w + 3) >> 2;
   const int tstart = j + 2 * k;
-  if (valid) {
+  const int S = W4 + h + 2 * K - 2;  // super-steps 0 .. (W4-1)+(h-1)+2(K-1)
+
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 nA[4], nB[4];                 // records of the next block
+  float4 nxt_u = z4, nxt_v = z4;       // previous-sweep du / dv of block I+1
+  float4 nx2_u = z4, nx2_v = z4;       // sweep 0: the same for block I+2 (global prefetch)
+  float4 nbot_u = z4, nbot_v = z4;     // sweep 0: bottom row, block I+1 (global prefetch)
+  bool nx2_ok = false;                 // nx2 holds a real block (else: beyond the row end -> zeros)
+  float2 nwf[4];                       // last sweep, last inner iteration: flow of block I+1
 #pragma unroll
-    for (int q = 0; q < PF; ++q) {
-      // column c is consumed at step tstart + c, slot (tstart + c) % PF
-      const int c = q;
-      const int slot = (tstart + c) % PF;
-      if (c < w) {
+  for (int c = 0; c < 4; ++c) nwf[c] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int s = 0; s < PF; ++s)
-          if (s == slot) {
-            ra[s] = __ldg(rec + (size_t)c * RF);
-            if (NOP == 2) rb[s] = __ldg(rec + (size_t)c * RF + 1);
-            if (k == 0) {
-              if (c + 1 < w) rr[s] = drow[c + 1];
-              if (j < h - 1) rbt[s] = drow[pitch + c];
-            }
-          }
-      }
-    }
-  }
-  float2 own = make_float2(0.f, 0.f);
-  if (valid && k == 0) own = drow[0];
+  for (int c = 0; c < 4; ++c) nA[c] = nB[c] = z4;
   float du_l = 0.f, dv_l = 0.f, hl = 0.f;
 
-  const int S = w + h + 2 * K - 3;  // last step: column w-1 of row h-1 in sweep K-1
-  for (int tb = 0; tb < S; tb += PF) {
+  // global prefetch issued at the end of super-step with block index I (clamped addresses)
+  auto prefetch = [&](int I) {
+    int nb = I + 1;
+    nb = nb < 0 ? 0 : (nb > W4 - 1 ? W4 - 1 : nb);
+    const float4* rp = recp + nb * bstep_r;
 #pragma unroll
-    for (int q = 0; q < PF; ++q) {
-      const int t = tb + q;
-      if (t < S) {
-        const int i = t - tstart;
-        float4* pprev = (t & 1) ? pub0 : pub1;
-        float4* pcur = (t & 1) ? pub1 : pub0;
-        if (valid && i >= -1 && i < w) {
-          // "right" neighbour = column i+1 of the previous sweep
-          float2 right = make_float2(0.f, 0.f);
-          if (k == 0) {
-            if (i < 0) right = own;            // column 0 was loaded before the loop
-            else if (i + 1 < w) right = rr[q];
-          } else if (i + 1 < w) {
-            const float4 v = pprev[(k - 1) * hb + j + 1];
-            right = make_float2(v.x, v.y);
-          }
-          if (i >= 0) {
-            const float4 A = ra[q];
-            float4 B = rb[q];
-            float2 bot = make_float2(0.f, 0.f);
-            if (j < h - 1) {
-              if (k == 0) bot = rbt[q];
-              else {
-                const float4 v = pprev[(k - 1) * hb + j + 2];
-                bot = make_float2(v.x, v.y);
-              }
-            }
-            float4 top = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j > 0) top = pprev[k * hb + j];
-            float du, dv = 0.f, svc;
-            if (NOP == 2) {
-              const float a11 = A.x, a12 = A.y, a22 = A.z, b1 = A.w, b2 = B.x, hh = B.y, vv = B.z;
-              const float vt = top.z;
-              float s1, s2;
-              if (j == 0) {
-                s1 = hh * right.x + vv * bot.x + b1;
-                s2 = hh * right.y + vv * bot.y + b2;
-              } else if (j == h - 1) {
-                s1 = hh * right.x + vt * top.x + b1;
-                s2 = hh * right.y + vt * top.y + b2;
-              } else {
-                s1 = hh * right.x + vt * top.x + vv * bot.x + b1;
-                s2 = hh * right.y + vt * top.y + vv * bot.y + b2;
-              }
-              float B1 = s1, B2 = s2;
-              if (i > 0) {
-                B1 = hl * du_l + s1;
-                B2 = hl * dv_l + s2;
-              }
-              du = own.x + omega * (a11 * B1 + a12 * B2 - own.x);
-              dv = own.y + omega * (a12 * B1 + a22 * B2 - own.y);
-              hl = hh;
-              svc = vv;
-            } else {
-              const float A11 = A.x, b1 = A.y, hh = A.z, vv = A.w;
-              float sigma = 0.0f;
-              if (j > 0) sigma -= top.z * top.x;
-              if (i > 0) sigma -= hl * du_l;
-              if (j < h - 1) sigma -= vv * bot.x;
-              if (i < w - 1) sigma -= hh * right.x;
-              const float B1 = b1 - sigma;
-              du = (1.0f - omega) * own.x + omega * (B1 / A11);
-              hl = hh;
-              svc = vv;
-            }
-            pcur[k * hb + j + 1] = make_float4(du, dv, svc, 0.f);
-            du_l = du;
-            dv_l = dv;
-            if (k == K - 1) {
-              drow[i] = make_float2(du, dv);
-              if (write_flow) {
-                if (NOP == 2) {
-                  float2* f2 = reinterpret_cast<float2*>(flow) + i;
-                  const float2 wv = *f2;
-                  *f2 = make_float2(wv.x + du, wv.y + dv);
-                } else {
-                  const float tsum = flow[i] + du;
-                  flow[i] = (g.camlr == 0) ? (tsum < 0.0f ? tsum : 0.0f) : (tsum > 0.0f ? tsum : 0.0f);
-                }
-              }
-            }
-            // refill this slot with column i+PF
-            const int c = i + PF;
-            if (c < w) {
-              ra[q] = __ldg(rec + (size_t)c * RF);
-              if (NOP == 2) rb[q] = __ldg(rec + (size_t)c * RF + 1);
-              if (k == 0) {
-                if (c + 1 < w) rr[q] = drow[c + 1];
-                if (j < h - 1) rbt[q] = drow[pitch + c];
-              }
-            }
-          }
-          own = right;
-        }
-        __syncthreads();
+    for (int c = 0; c < 4; ++c) {
+      nA[c] = __ldg(rp + (c * RF) * hpad);
+      if (NOP == 2) nB[c] = __ldg(rp + (c * RF + 1) * hpad);
+    }
+    if (k0) {
+      nbot_u = dbot4[nb * bstep_d];            // du x4
+      if (NOP == 2) nbot_v = dbot4[nb * bstep_d + hpad];  // dv x4
+      int n2 = I + 2;
+      const bool n2ok = (n2 >= 0) & (n2 < W4);
+      n2 = n2 < 0 ? 0 : (n2 > W4 - 1 ? W4 - 1 : n2);
+      nx2_u = drow4[n2 * bstep_d];
+      if (NOP == 2) nx2_v = drow4[n2 * bstep_d + hpad];
+      nx2_ok = n2ok;
+    }
+    if (write_flow && klast) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        int col = 4 * nb + c;
+        col = col > w - 1 ? w - 1 : col;
+        if (NOP == 2) nwf[c] = reinterpret_cast<const float2*>(flow)[col];
+        else nwf[c].x = flow[col];
       }
     }
+  };
+  // emulate super-steps -2 and -1 so that the first rows of sweep 0 find their data in place
+  prefetch(-2 - tstart);
+  nxt_u = nx2_ok ? nx2_u : z4;
+  nxt_v = nx2_ok ? nx2_v : z4;
+  prefetch(-1 - tstart);
+
+  int I = -tstart;
+  unsigned prevb = bufbytes, curb = 0;   // T even: write buffer 0, read buffer 1
+#pragma unroll 1
+  for (int T = 0; T < S; ++T, ++I) {
+    const bool in_range = valid & (I >= 0) & (I < W4);
+    // ---- shift the register pipeline / read the board -----------------------------
+    const float4 own_u = nxt_u, own_v = nxt_v;
+    float4 bot_u, bot_v = z4;
+    float2 wf[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) wf[c] = nwf[c];
+    if (k0) {
+      nxt_u = nx2_ok ? nx2_u : z4;
+      nxt_v = nx2_ok ? nx2_v : z4;
+      bot_u = nbot_u;
+      bot_v = nbot_v;
+    } else {
+      nxt_u = lds128(a_right + prevb);
+      bot_u = lds128(a_bot + prevb);
+      if (NOP == 2) {
+        nxt_v = lds128(a_right + prevb + 16);
+        bot_v = lds128(a_bot + prevb + 16);
+      }
+    }
+    const float4 top_u = lds128(a_top + prevb);
+    const float4 top_v = (NOP == 2) ? lds128(a_top + prevb + 16) : z4;
+    const float4 top_s = lds128(a_top + prevb + (NF - 1) * 16);
+    const float ou[5] = {own_u.x, own_u.y, own_u.z, own_u.w, nxt_u.x};
+    const float ov[5] = {own_v.x, own_v.y, own_v.z, own_v.w, nxt_v.x};
+    const float tu[4] = {top_u.x, top_u.y, top_u.z, top_u.w};
+    const float tv[4] = {top_v.x, top_v.y, top_v.z, top_v.w};
+    const float ts[4] = {top_s.x, top_s.y, top_s.z, top_s.w};
+    const float bu[4] = {bot_u.x, bot_u.y, bot_u.z, bot_u.w};
+    const float bv[4] = {bot_v.x, bot_v.y, bot_v.z, bot_v.w};
+    float nu[4], nv[4], ns[4];
+    const int col0 = 4 * I;
+    if (NOP == 2) {
+      // everything that does not depend on the left neighbour first (ILP) ...
+      float s1[4], s2[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool has_r = (col0 + c + 1 < w);
+        const float du_r = has_r ? ou[c + 1] : 0.0f, dv_r = has_r ? ov[c + 1] : 0.0f;
+        const float b1 = nA[c].w, b2 = nB[c].x, hh = nB[c].y, vv = nB[c].z;
+        // solver.c:204-205 (middle lines), :122-123 (first line), :259-260 (last line)
+        const float t1u = hh * du_r, t1v = hh * dv_r;
+        const float t2u = t1u + ts[c] * tu[c], t2v = t1v + ts[c] * tv[c];
+        const float bsu = first_row ? t1u : t2u, bsv = first_row ? t1v : t2v;
+        const float t3u = bsu + vv * bu[c], t3v = bsv + vv * bv[c];
+        s1[c] = (last_row ? bsu : t3u) + b1;
+        s2[c] = (last_row ? bsv : t3v) + b2;
+        ns[c] = vv;
+      }
+      // ... then the sequential recurrence along the row (solver.c:206-210)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float a11 = nA[c].x, a12 = nA[c].y, a22 = nA[c].z;
+        const float B1w = hl * du_l + s1[c], B2w = hl * dv_l + s2[c];
+        const bool has_l = (col0 + c > 0);
+        const float B1 = has_l ? B1w : s1[c], B2 = has_l ? B2w : s2[c];
+        du_l = ou[c] + omega * (a11 * B1 + a12 * B2 - ou[c]);
+        dv_l = ov[c] + omega * (a12 * B1 + a22 * B2 - ov[c]);
+        hl = nB[c].y;
+        nu[c] = du_l;
+        nv[c] = dv_l;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int col = col0 + c;
+        const float du_r = ou[c + 1];
+        const float A11 = nA[c].x, b1 = nA[c].y, hh = nA[c].z, vv = nA[c].w;
+        // solver.c:438-462: sigma accumulates top, left, bottom, right
+        float sg = 0.0f;
+        const float s_t = sg - ts[c] * tu[c];
+        sg = first_row ? sg : s_t;
+        const float s_l = sg - hl * du_l;
+        sg = (col > 0) ? s_l : sg;
+        const float s_b = sg - vv * bu[c];
+        sg = last_row ? sg : s_b;
+        const float s_r = sg - hh * du_r;
+        sg = (col < w - 1) ? s_r : sg;
+        const float B1 = b1 - sg;
+        du_l = (1.0f - omega) * ou[c] + omega * (B1 / A11);
+        hl = hh;
+        nu[c] = du_l;
+        nv[c] = 0.f;
+        ns[c] = vv;
+      }
+    }
+    sts128(a_me + curb, make_float4(nu[0], nu[1], nu[2], nu[3]));
+    if (NOP == 2) sts128(a_me + curb + 16, make_float4(nv[0], nv[1], nv[2], nv[3]));
+    sts128(a_me + curb + (NF - 1) * 16, make_float4(ns[0], ns[1], ns[2], ns[3]));
+    if (klast && in_range) {
+      drow4[I * bstep_d] = make_float4(nu[0], nu[1], nu[2], nu[3]);
+      if (NOP == 2) drow4[I * bstep_d + hpad] = make_float4(nv[0], nv[1], nv[2], nv[3]);
+      if (write_flow) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col = col0 + c;
+          if (col < w) {
+            if (NOP == 2) {
+              float2* f2 = reinterpret_cast<float2*>(flow) + col;
+              const float2 wv = *f2;
+              *f2 = make_float2(wv.x + nu[c], wv.y + nv[c]);
+            } else {
+              const float tsum = flow[col] + nu[c];
+              flow[col] = (g.camlr == 0) ? (tsum < 0.0f ? tsum : 0.0f) : (tsum > 0.0f ? tsum : 0.0f);
+            }
+          }
+        }
+      }
+    }
+    prefetch(I);
+    __syncthreads();
+    const unsigned tmp = prevb;
+    prevb = curb;
+    curb = tmp;
   }
 }
 
@@ -513,19 +589,22 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
     warp_kernel<C, NOP><<<grid, block, 0, st>>>(g, pl, f0);
     deriv1_kernel<C><<<gridc, block, 0, st>>>(g, pl);
     deriv2_kernel<C><<<gridc, block, 0, st>>>(g, pl);
-    cudaMemsetAsync(pl.dudv, 0, sizeof(float2) * pl.plane * nf, st);
+    cudaMemsetAsync(pl.dudv, 0, sizeof(float4) * pl.dudv_stride * nf, st);
   }
   launches += 3;
-  // sweeps per SOR launch: all of them when (sweeps x rows) fits one CTA
+  // sweeps per SOR launch: all of them when (sweeps x padded rows) fits a 512-thread CTA (128
+  // registers per thread); otherwise one sweep per launch, 1024-thread variant for tall levels.
   const int K = vp.n_solver;
-  const bool fused = (K >= 1) && (K * g.h <= 1024);
+  const int hpad = ((g.h + 31) / 32) * 32;
+  const bool fused = (K >= 1) && (K * hpad <= 512);
   const int kl = fused ? K : 1;
-  const int nthreads = ((kl * g.h + 31) / 32) * 32;
-  const size_t smem = sizeof(float4) * 2 * kl * (g.h + 2);
+  const int nthreads = kl * hpad;
+  const int nf4 = (NOP == 2) ? 3 : 2;
+  const size_t smem = sizeof(float4) * 2 * kl * (g.h + 2) * nf4;
   const bool big = nthreads > 512;
   if (K >= 1) {
-    if (big) cudaFuncSetAttribute(sor_kernel<NOP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else cudaFuncSetAttribute(sor_kernel<NOP, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (big) cudaFuncSetAttribute(sor_kernel<NOP, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else cudaFuncSetAttribute(sor_kernel<NOP, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   for (int it = 0; it < vp.n_inner; ++it) {
     {
@@ -538,8 +617,8 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
     for (int s = 0; s < nl; ++s) {
       const int wf = (last && s == nl - 1) ? 1 : 0;
       ProfScope scope(prof, KC_VR_SOR);
-      if (big) sor_kernel<NOP, 2><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, wf);
-      else sor_kernel<NOP, 8><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, wf);
+      if (big) sor_kernel<NOP, 1024><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad, wf);
+      else sor_kernel<NOP, 512><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad, wf);
       ++launches;
     }
   }
