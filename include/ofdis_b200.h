@@ -81,6 +81,14 @@ int ofdis_destroy(ofdis_ctx* ctx);
 const char* ofdis_last_error(const ofdis_ctx* ctx);
 const char* ofdis_version(void);
 
+/* camparam::camlr (oflow.h:28; 0 = left/forward grid clamps disparity <= 0, 1 = right/backward
+ * clamps >= 0, patch.cpp:188-193, refine_variational.cpp:299-314).  Default 0, as OFClass's
+ * forward grid uses.  Only meaningful for nop == 1. */
+int ofdis_set_camlr(ofdis_ctx* ctx, int camlr);
+/* optparam::dp_thresh is stored SQUARED by OFClass (oflow.cpp:88); callers that already hold
+ * the squared value (PatGridClass built from an optparam) set it here bit-exactly. */
+int ofdis_set_dp_thresh_sq(ofdis_ctx* ctx, float dp_thresh_sq);
+
 /* level geometry (oflow.cpp:142-151, patchgrid.cpp:42-48) */
 int ofdis_level_info(const ofdis_ctx* ctx, int level, int* w, int* h, int* nopw, int* noph, int* steps);
 

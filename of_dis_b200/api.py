@@ -28,6 +28,7 @@ EXPORTS = [
     "ofdis_patgrid_optimize", "ofdis_patgrid_aggregate", "ofdis_varref_refine", "ofdis_run", "ofdis_sync",
     "ofdis_get_flow", "ofdis_set_flow", "ofdis_get_flow_batch", "ofdis_get_patches", "ofdis_debug_get",
     "ofdis_debug_varref_iters", "ofdis_launch_count", "ofdis_set_graph_mode", "ofdis_profile_run",
+    "ofdis_set_camlr", "ofdis_set_dp_thresh_sq",
 ]
 
 
@@ -74,6 +75,8 @@ def lib():
         L.ofdis_get_patches.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4
         L.ofdis_debug_get.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
         L.ofdis_set_graph_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.ofdis_set_camlr.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.ofdis_set_dp_thresh_sq.argtypes = [ctypes.c_void_p, ctypes.c_float]
         L.ofdis_profile_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         _lib = L
     return _lib
@@ -199,6 +202,9 @@ class Context:
 
     def sync(self):
         self._ck(lib().ofdis_sync(self._h))
+
+    def set_camlr(self, camlr: int):
+        self._ck(lib().ofdis_set_camlr(self._h, camlr))
 
     def set_graph_mode(self, on: bool):
         self._ck(lib().ofdis_set_graph_mode(self._h, 1 if on else 0))

@@ -53,5 +53,33 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+BINDIR = os.path.join(HERE, "bin")
+HOST = os.path.join(HERE, "host")
+CLI_TARGETS = {"run_OF_INT": (1, 1), "run_OF_RGB": (1, 3), "run_DE_INT": (2, 1), "run_DE_RGB": (2, 3)}
+
+
+def build_host(force: bool = False) -> str:
+    """The reference's four command-line binaries (CMakeLists.txt:25-46) plus the C++
+    self-test, g++ against libofdis_b200.so (rpath $ORIGIN/../lib)."""
+    build(force=False)
+    os.makedirs(BINDIR, exist_ok=True)
+    srcs = [os.path.join(HOST, f) for f in ("ofdis_host.cpp", "ofdis_host.h", "run_dense.cpp", "host_selftest.cpp")]
+    newest = max(os.path.getmtime(f) for f in srcs + [LIB])
+    common = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", os.path.join(HOST, "ofdis_host.cpp")]
+    link = ["-L" + LIBDIR, "-lofdis_b200", "-lz", "-Wl,-rpath,$ORIGIN/../lib"]
+    jobs = {name: common + [os.path.join(HOST, "run_dense.cpp"), "-DSELECTMODE=%d" % m, "-DSELECTCHANNEL=%d" % c]
+            for name, (m, c) in CLI_TARGETS.items()}
+    jobs["ofdis_host_selftest"] = common + [os.path.join(HOST, "host_selftest.cpp")]
+    for name, cmd in jobs.items():
+        out = os.path.join(BINDIR, name)
+        if force or not os.path.exists(out) or os.path.getmtime(out) < newest:
+            res = subprocess.run(cmd + ["-o", out] + link, capture_output=True, text=True)
+            if res.returncode:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError("g++ failed building %s" % name)
+    return BINDIR
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

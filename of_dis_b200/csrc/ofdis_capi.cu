@@ -254,6 +254,22 @@ int ofdis_destroy(ofdis_ctx* ctx) {
   return OFDIS_OK;
 }
 
+int ofdis_set_camlr(ofdis_ctx* ctx, int camlr) {
+  if (!ctx || (camlr != 0 && camlr != 1)) return OFDIS_ERR_ARG;
+  for (LevelGeom& L : ctx->lev) L.camlr = camlr;
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);  // kernel arguments changed
+  ctx->graphs.clear();
+  return OFDIS_OK;
+}
+
+int ofdis_set_dp_thresh_sq(ofdis_ctx* ctx, float dp_thresh_sq) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  ctx->pp.dp_thresh_sq = dp_thresh_sq;
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  ctx->graphs.clear();
+  return OFDIS_OK;
+}
+
 int ofdis_level_info(const ofdis_ctx* ctx, int level, int* w, int* h, int* nopw, int* noph, int* steps) {
   if (!ctx) return OFDIS_ERR_ARG;
   const LevelGeom* L = level_of(const_cast<ofdis_ctx*>(ctx), level);
