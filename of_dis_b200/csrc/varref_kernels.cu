@@ -359,6 +359,19 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// volatile: one load per call site and per execution -- ptxas otherwise re-materialises
+// ld.global.nc values after the barrier instead of keeping them in registers, which puts an
+// L2 round trip at the head of every super-step
+__device__ __forceinline__ float4 ldg128(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg128_rw(const float4* p) {  // data written earlier in this kernel family
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -367,15 +380,28 @@ __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
 // it the "sweep 0 reads global / last sweep writes global" roles) is uniform per warp.
 // Out-of-range super-steps execute the same straight-line code on clamped addresses and
 // simply do not store to global memory; whatever they put on the board is never consumed
-// by an in-range neighbour (SOR schedule).
+// by an in-range neighbour.
+//
+// Register pipeline: two parity sets.  Everything a super-step T needs from global memory
+// (its block's records; for sweep 0 the previous values of its block and of the row below;
+// for the final write the flow) sits in set[T&1], loaded at the end of super-step T-2
+// straight into its final registers (prefetch distance 2, no copies).  The other set holds
+// block I+1, whose first column is the right neighbour of this block's last column.
+struct SorSet {
+  float4 A[4], B[4];     // records of the block (B unused for stereo)
+  float4 own_u, own_v;   // previous-sweep du / dv of the block
+  float4 bot_u, bot_v;   // sweep 0: previous du / dv of the row below
+  float2 wf[4];          // last sweep of the last inner iteration: flow of the block
+};
+
 template <int NOP, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+__global__ void __launch_bounds__(MAXT, 1)
     sor_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int f0, int K, int hpad, int write_flow) {
   extern __shared__ float4 s_pub[];  // [2][K][h+2][NF]
   constexpr int NF = (NOP == 2) ? 3 : 2;   // float4 per board entry: du x4, (dv x4), sv x4
   constexpr int RF = (NOP == 2) ? 2 : 1;   // float4 per pixel record
   const int fr = blockIdx.x, frame = f0 + fr;
-  const int w = g.w, h = g.h, pitch = g.pitch;
+  const int w = g.w, h = g.h;
   const int tid = threadIdx.x;
   const int k = tid / hpad, jraw = tid - k * hpad;
   const bool valid = jraw < h;
@@ -390,6 +416,7 @@ __global__ void __launch_bounds__(MAXT)
   const unsigned a_bot = sbase + (unsigned)((km * hb + j + 2) * NF) * 16u;
   const bool first_row = (j == 0), last_row = (j == h - 1);
   const bool k0 = (k == 0), klast = (k == K - 1);
+  const bool do_flow = klast && write_flow;
   const float omega = vp.omega;
 
   // skewed arrays: block (I, j) float4 q at ((I + j) * NQ + q) * hpad + j
@@ -404,90 +431,62 @@ __global__ void __launch_bounds__(MAXT)
   const int W4 = (w + 3) >> 2;
   const int tstart = j + 2 * k;
   const int S = W4 + h + 2 * K - 2;  // super-steps 0 .. (W4-1)+(h-1)+2(K-1)
-
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 nA[4], nB[4];                 // records of the next block
-  float4 nxt_u = z4, nxt_v = z4;       // previous-sweep du / dv of block I+1
-  float4 nx2_u = z4, nx2_v = z4;       // sweep 0: the same for block I+2 (global prefetch)
-  float4 nbot_u = z4, nbot_v = z4;     // sweep 0: bottom row, block I+1 (global prefetch)
-  bool nx2_ok = false;                 // nx2 holds a real block (else: beyond the row end -> zeros)
-  float2 nwf[4];                       // last sweep, last inner iteration: flow of block I+1
-#pragma unroll
-  for (int c = 0; c < 4; ++c) nwf[c] = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) nA[c] = nB[c] = z4;
-  float du_l = 0.f, dv_l = 0.f, hl = 0.f;
 
-  // global prefetch issued at the end of super-step with block index I (clamped addresses)
-  auto prefetch = [&](int I) {
-    int nb = I + 1;
-    nb = nb < 0 ? 0 : (nb > W4 - 1 ? W4 - 1 : nb);
+  // loads block `blk` (clamped) into a parity set
+  auto load_set = [&](SorSet& s, int blk) {
+    const int nb = blk < 0 ? 0 : (blk > W4 - 1 ? W4 - 1 : blk);
     const float4* rp = recp + nb * bstep_r;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      nA[c] = __ldg(rp + (c * RF) * hpad);
-      if (NOP == 2) nB[c] = __ldg(rp + (c * RF + 1) * hpad);
+      s.A[c] = ldg128(rp + (c * RF) * hpad);
+      if (NOP == 2) s.B[c] = ldg128(rp + (c * RF + 1) * hpad);
     }
     if (k0) {
-      nbot_u = dbot4[nb * bstep_d];            // du x4
-      if (NOP == 2) nbot_v = dbot4[nb * bstep_d + hpad];  // dv x4
-      int n2 = I + 2;
-      const bool n2ok = (n2 >= 0) & (n2 < W4);
-      n2 = n2 < 0 ? 0 : (n2 > W4 - 1 ? W4 - 1 : n2);
-      nx2_u = drow4[n2 * bstep_d];
-      if (NOP == 2) nx2_v = drow4[n2 * bstep_d + hpad];
-      nx2_ok = n2ok;
+      // beyond the row end the right neighbour is 0 (solver.c:96-99): handled by has_r below,
+      // so the clamped load needs no masking here
+      s.own_u = ldg128_rw(drow4 + nb * bstep_d);
+      s.bot_u = ldg128_rw(dbot4 + nb * bstep_d);
+      if (NOP == 2) {
+        s.own_v = ldg128_rw(drow4 + nb * bstep_d + hpad);
+        s.bot_v = ldg128_rw(dbot4 + nb * bstep_d + hpad);
+      }
     }
-    if (write_flow && klast) {
+    if (do_flow) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         int col = 4 * nb + c;
         col = col > w - 1 ? w - 1 : col;
-        if (NOP == 2) nwf[c] = reinterpret_cast<const float2*>(flow)[col];
-        else nwf[c].x = flow[col];
+        if (NOP == 2) s.wf[c] = reinterpret_cast<const float2*>(flow)[col];
+        else s.wf[c].x = flow[col];
       }
     }
   };
-  // emulate super-steps -2 and -1 so that the first rows of sweep 0 find their data in place
-  prefetch(-2 - tstart);
-  nxt_u = nx2_ok ? nx2_u : z4;
-  nxt_v = nx2_ok ? nx2_v : z4;
-  prefetch(-1 - tstart);
 
-  int I = -tstart;
+  float du_l = 0.f, dv_l = 0.f, hl = 0.f;
   unsigned prevb = bufbytes, curb = 0;   // T even: write buffer 0, read buffer 1
-#pragma unroll 1
-  for (int T = 0; T < S; ++T, ++I) {
+
+  // one super-step: `cur` holds block I, `nxt` block I+1
+  auto step = [&](SorSet& cur, SorSet& nxt, int I) {
     const bool in_range = valid & (I >= 0) & (I < W4);
-    // ---- shift the register pipeline / read the board -----------------------------
-    const float4 own_u = nxt_u, own_v = nxt_v;
-    float4 bot_u, bot_v = z4;
-    float2 wf[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) wf[c] = nwf[c];
-    if (k0) {
-      nxt_u = nx2_ok ? nx2_u : z4;
-      nxt_v = nx2_ok ? nx2_v : z4;
-      bot_u = nbot_u;
-      bot_v = nbot_v;
-    } else {
-      nxt_u = lds128(a_right + prevb);
-      bot_u = lds128(a_bot + prevb);
+    if (!k0) {  // previous-sweep values come from the board (written one super-step ago)
+      nxt.own_u = lds128(a_right + prevb);
+      cur.bot_u = lds128(a_bot + prevb);
       if (NOP == 2) {
-        nxt_v = lds128(a_right + prevb + 16);
-        bot_v = lds128(a_bot + prevb + 16);
+        nxt.own_v = lds128(a_right + prevb + 16);
+        cur.bot_v = lds128(a_bot + prevb + 16);
       }
     }
     const float4 top_u = lds128(a_top + prevb);
     const float4 top_v = (NOP == 2) ? lds128(a_top + prevb + 16) : z4;
     const float4 top_s = lds128(a_top + prevb + (NF - 1) * 16);
-    const float ou[5] = {own_u.x, own_u.y, own_u.z, own_u.w, nxt_u.x};
-    const float ov[5] = {own_v.x, own_v.y, own_v.z, own_v.w, nxt_v.x};
+    const float ou[5] = {cur.own_u.x, cur.own_u.y, cur.own_u.z, cur.own_u.w, nxt.own_u.x};
+    const float ov[5] = {cur.own_v.x, cur.own_v.y, cur.own_v.z, cur.own_v.w, nxt.own_v.x};
     const float tu[4] = {top_u.x, top_u.y, top_u.z, top_u.w};
     const float tv[4] = {top_v.x, top_v.y, top_v.z, top_v.w};
     const float ts[4] = {top_s.x, top_s.y, top_s.z, top_s.w};
-    const float bu[4] = {bot_u.x, bot_u.y, bot_u.z, bot_u.w};
-    const float bv[4] = {bot_v.x, bot_v.y, bot_v.z, bot_v.w};
+    const float bu[4] = {cur.bot_u.x, cur.bot_u.y, cur.bot_u.z, cur.bot_u.w};
+    const float bv[4] = {cur.bot_v.x, cur.bot_v.y, cur.bot_v.z, cur.bot_v.w};
     float nu[4], nv[4], ns[4];
     const int col0 = 4 * I;
     if (NOP == 2) {
@@ -497,7 +496,7 @@ __global__ void __launch_bounds__(MAXT)
       for (int c = 0; c < 4; ++c) {
         const bool has_r = (col0 + c + 1 < w);
         const float du_r = has_r ? ou[c + 1] : 0.0f, dv_r = has_r ? ov[c + 1] : 0.0f;
-        const float b1 = nA[c].w, b2 = nB[c].x, hh = nB[c].y, vv = nB[c].z;
+        const float b1 = cur.A[c].w, b2 = cur.B[c].x, hh = cur.B[c].y, vv = cur.B[c].z;
         // solver.c:204-205 (middle lines), :122-123 (first line), :259-260 (last line)
         const float t1u = hh * du_r, t1v = hh * dv_r;
         const float t2u = t1u + ts[c] * tu[c], t2v = t1v + ts[c] * tv[c];
@@ -510,13 +509,13 @@ __global__ void __launch_bounds__(MAXT)
       // ... then the sequential recurrence along the row (solver.c:206-210)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float a11 = nA[c].x, a12 = nA[c].y, a22 = nA[c].z;
+        const float a11 = cur.A[c].x, a12 = cur.A[c].y, a22 = cur.A[c].z;
         const float B1w = hl * du_l + s1[c], B2w = hl * dv_l + s2[c];
         const bool has_l = (col0 + c > 0);
         const float B1 = has_l ? B1w : s1[c], B2 = has_l ? B2w : s2[c];
         du_l = ou[c] + omega * (a11 * B1 + a12 * B2 - ou[c]);
         dv_l = ov[c] + omega * (a12 * B1 + a22 * B2 - ov[c]);
-        hl = nB[c].y;
+        hl = cur.B[c].y;
         nu[c] = du_l;
         nv[c] = dv_l;
       }
@@ -525,7 +524,7 @@ __global__ void __launch_bounds__(MAXT)
       for (int c = 0; c < 4; ++c) {
         const int col = col0 + c;
         const float du_r = ou[c + 1];
-        const float A11 = nA[c].x, b1 = nA[c].y, hh = nA[c].z, vv = nA[c].w;
+        const float A11 = cur.A[c].x, b1 = cur.A[c].y, hh = cur.A[c].z, vv = cur.A[c].w;
         // solver.c:438-462: sigma accumulates top, left, bottom, right
         float sg = 0.0f;
         const float s_t = sg - ts[c] * tu[c];
@@ -556,22 +555,37 @@ __global__ void __launch_bounds__(MAXT)
           const int col = col0 + c;
           if (col < w) {
             if (NOP == 2) {
-              float2* f2 = reinterpret_cast<float2*>(flow) + col;
-              const float2 wv = *f2;
-              *f2 = make_float2(wv.x + nu[c], wv.y + nv[c]);
+              reinterpret_cast<float2*>(flow)[col] = make_float2(cur.wf[c].x + nu[c], cur.wf[c].y + nv[c]);
             } else {
-              const float tsum = flow[col] + nu[c];
+              const float tsum = cur.wf[c].x + nu[c];
               flow[col] = (g.camlr == 0) ? (tsum < 0.0f ? tsum : 0.0f) : (tsum > 0.0f ? tsum : 0.0f);
             }
           }
         }
       }
     }
-    prefetch(I);
+    load_set(cur, I + 2);  // `cur` is dead now: refill it for super-step T+2
     __syncthreads();
     const unsigned tmp = prevb;
     prevb = curb;
     curb = tmp;
+  };
+
+  SorSet s0, s1;
+  s0.own_u = s0.own_v = s0.bot_u = s0.bot_v = z4;
+  s1.own_u = s1.own_v = s1.bot_u = s1.bot_v = z4;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    s0.B[c] = s1.B[c] = z4;
+    s0.wf[c] = s1.wf[c] = make_float2(0.f, 0.f);
+  }
+  load_set(s0, -tstart);      // block of super-step 0
+  load_set(s1, 1 - tstart);   // block of super-step 1
+  int I = -tstart;
+#pragma unroll 1
+  for (int T = 0; T < S; T += 2, I += 2) {
+    step(s0, s1, I);
+    if (T + 1 < S) step(s1, s0, I + 1);
   }
 }
 
@@ -601,10 +615,13 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   const int nthreads = kl * hpad;
   const int nf4 = (NOP == 2) ? 3 : 2;
   const size_t smem = sizeof(float4) * 2 * kl * (g.h + 2) * nf4;
-  const bool big = nthreads > 512;
+  // register budget follows the CTA size: <=256 threads -> up to 255 registers (no reuse of
+  // in-flight load destinations), <=512 -> 128, else 64 (spills; only for very tall levels)
+  const int variant = nthreads <= 256 ? 0 : (nthreads <= 512 ? 1 : 2);
   if (K >= 1) {
-    if (big) cudaFuncSetAttribute(sor_kernel<NOP, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else cudaFuncSetAttribute(sor_kernel<NOP, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (variant == 0) cudaFuncSetAttribute(sor_kernel<NOP, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else if (variant == 1) cudaFuncSetAttribute(sor_kernel<NOP, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else cudaFuncSetAttribute(sor_kernel<NOP, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   for (int it = 0; it < vp.n_inner; ++it) {
     {
@@ -617,8 +634,9 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
     for (int s = 0; s < nl; ++s) {
       const int wf = (last && s == nl - 1) ? 1 : 0;
       ProfScope scope(prof, KC_VR_SOR);
-      if (big) sor_kernel<NOP, 1024><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad, wf);
-      else sor_kernel<NOP, 512><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad, wf);
+      if (variant == 0) sor_kernel<NOP, 256><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad, wf);
+      else if (variant == 1) sor_kernel<NOP, 512><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad, wf);
+      else sor_kernel<NOP, 1024><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad, wf);
       ++launches;
     }
   }
