@@ -506,18 +506,40 @@ __global__ void __launch_bounds__(MAXT, 1)
         s2[c] = (last_row ? bsv : t3v) + b2;
         ns[c] = vv;
       }
+      // the block's records are needed no further except a11,a12,a22,sh: keep those, refill the
+      // set for super-step T+2 now, so the loads fly while the recurrence below keeps the
+      // pipeline latency-bound anyway
+      float ca11[4], ca12[4], ca22[4], chh[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ca11[c] = cur.A[c].x;
+        ca12[c] = cur.A[c].y;
+        ca22[c] = cur.A[c].z;
+        chh[c] = cur.B[c].y;
+      }
+      float wfx[4], wfy[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        wfx[c] = cur.wf[c].x;
+        wfy[c] = cur.wf[c].y;
+      }
+      load_set(cur, I + 2);
       // ... then the sequential recurrence along the row (solver.c:206-210)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float a11 = cur.A[c].x, a12 = cur.A[c].y, a22 = cur.A[c].z;
         const float B1w = hl * du_l + s1[c], B2w = hl * dv_l + s2[c];
         const bool has_l = (col0 + c > 0);
         const float B1 = has_l ? B1w : s1[c], B2 = has_l ? B2w : s2[c];
-        du_l = ou[c] + omega * (a11 * B1 + a12 * B2 - ou[c]);
-        dv_l = ov[c] + omega * (a12 * B1 + a22 * B2 - ov[c]);
-        hl = cur.B[c].y;
+        du_l = ou[c] + omega * (ca11[c] * B1 + ca12[c] * B2 - ou[c]);
+        dv_l = ov[c] + omega * (ca12[c] * B1 + ca22[c] * B2 - ov[c]);
+        hl = chh[c];
         nu[c] = du_l;
         nv[c] = dv_l;
+      }
+      if (klast && in_range && write_flow) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (col0 + c < w) reinterpret_cast<float2*>(flow)[col0 + c] = make_float2(wfx[c] + nu[c], wfy[c] + nv[c]);
       }
     } else {
 #pragma unroll
@@ -542,6 +564,15 @@ __global__ void __launch_bounds__(MAXT, 1)
         nv[c] = 0.f;
         ns[c] = vv;
       }
+      if (klast && in_range && write_flow) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (col0 + c < w) {
+            const float tsum = cur.wf[c].x + nu[c];
+            flow[col0 + c] = (g.camlr == 0) ? (tsum < 0.0f ? tsum : 0.0f) : (tsum > 0.0f ? tsum : 0.0f);
+          }
+      }
+      load_set(cur, I + 2);
     }
     sts128(a_me + curb, make_float4(nu[0], nu[1], nu[2], nu[3]));
     if (NOP == 2) sts128(a_me + curb + 16, make_float4(nv[0], nv[1], nv[2], nv[3]));
@@ -549,22 +580,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     if (klast && in_range) {
       drow4[I * bstep_d] = make_float4(nu[0], nu[1], nu[2], nu[3]);
       if (NOP == 2) drow4[I * bstep_d + hpad] = make_float4(nv[0], nv[1], nv[2], nv[3]);
-      if (write_flow) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int col = col0 + c;
-          if (col < w) {
-            if (NOP == 2) {
-              reinterpret_cast<float2*>(flow)[col] = make_float2(cur.wf[c].x + nu[c], cur.wf[c].y + nv[c]);
-            } else {
-              const float tsum = cur.wf[c].x + nu[c];
-              flow[col] = (g.camlr == 0) ? (tsum < 0.0f ? tsum : 0.0f) : (tsum > 0.0f ? tsum : 0.0f);
-            }
-          }
-        }
-      }
     }
-    load_set(cur, I + 2);  // `cur` is dead now: refill it for super-step T+2
     __syncthreads();
     const unsigned tmp = prevb;
     prevb = curb;
