@@ -35,6 +35,7 @@ import numpy as np  # noqa: E402
 
 H_ORG, W_ORG = 436, 1024
 OP_POINT = 2
+MAX_DISTINCT = 16
 
 
 def make_pairs(n, seed0):
@@ -42,9 +43,11 @@ def make_pairs(n, seed0):
 
     prm = params.operating_point(OP_POINT, W_ORG)
     pyrs = []
-    for s in range(n):
+    for s in range(min(n, MAX_DISTINCT)):
         i0, i1, _ = synth.synthetic_pair(H_ORG, W_ORG, 1, seed=seed0 + s)
         pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
+    while len(pyrs) < n:  # large batches cycle through the distinct pairs (generation costs 0.3 s each)
+        pyrs.append(pyrs[len(pyrs) % MAX_DISTINCT])
     return prm, pyrs
 
 

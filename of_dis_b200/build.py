@@ -43,7 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = ["-DOFDIS_SOR_TIMING"] if os.environ.get("OFDIS_SOR_TIMING") else []
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode:

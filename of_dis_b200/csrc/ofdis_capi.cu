@@ -213,7 +213,7 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
     const size_t plane = (size_t)Lf.pitch * Lf.h;
     const int C = prm->noc;
     // skewed SOR arrays: (W4 + h) diagonals x hpad rows, 8 (rec) + 2 (dudv) float4 per block
-    const size_t diag = (size_t)((Lf.w + 3) / 4 + Lf.h) * (((Lf.h + 31) / 32) * 32);
+    const size_t diag = (size_t)((Lf.w + 3) / 4 + Lf.h + 2) * (((Lf.h + 31) / 32) * 32);
     const size_t per_frame = plane * (1 + C + 8 * C) + diag * 4 * (8 + 2);
     ok = dalloc((void**)&ctx->d_planes, sizeof(float) * per_frame * max_frames);
     if (ok) {
@@ -349,7 +349,7 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   pl.plane = (size_t)L->pitch * L->h;
   pl.hpad = ((L->h + 31) / 32) * 32;
   {
-    const size_t diag = (size_t)((L->w + 3) / 4 + L->h) * pl.hpad;
+    const size_t diag = (size_t)((L->w + 3) / 4 + L->h + 2) * pl.hpad;
     pl.rec_stride = diag * (L->nop == 2 ? 8 : 4);
     pl.dudv_stride = diag * 2;
   }
@@ -474,7 +474,7 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
     const int hpad = ((L->h + 31) / 32) * 32, W4 = (L->w + 3) / 4;
     const int nq = is_rec ? (L->nop == 2 ? 8 : 4) : 2;            // float4 per 4-pixel block
     const int per = is_rec ? (L->nop == 2 ? 8 : 4) : 2;           // floats per pixel
-    const size_t stride = (size_t)(W4 + L->h) * hpad * nq;        // float4 per frame
+    const size_t stride = (size_t)(W4 + L->h + 2) * hpad * nq;    // float4 per frame
     if (plane * per > max_floats) return OFDIS_ERR_ARG;
     std::vector<float> raw(stride * 4);
     const float4* base = (is_rec ? ctx->planes.rec : ctx->planes.dudv) + (size_t)fr * stride;

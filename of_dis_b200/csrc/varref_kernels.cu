@@ -369,7 +369,13 @@ __device__ __forceinline__ float4 ldg128(const float4* p) {
 }
 __device__ __forceinline__ float4 ldg128_rw(const float4* p) {  // data written earlier in this kernel family
   float4 v;
+#if defined(OFDIS_RW_NC)
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#elif defined(OFDIS_RW_CG)
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#else
   asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#endif
   return v;
 }
 __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
@@ -387,22 +393,66 @@ __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
 // for the final write the flow) sits in set[T&1], loaded at the end of super-step T-2
 // straight into its final registers (prefetch distance 2, no copies).  The other set holds
 // block I+1, whose first column is the right neighbour of this block's last column.
+#ifdef OFDIS_SOR_TIMING
+// debug build only: per-warp cycle stamps of a few super-steps of frame 0 (tools/sor_timing.py)
+__device__ long long g_sor_times[64 * 8 * 16];
+#define SOR_STAMP(slot, dep1, dep2)                                                           \
+  do {                                                                                        \
+    if (fr == 0 && (tid & 31) == 0 && T >= 40 && T < 48) {                                    \
+      long long t__;                                                                          \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t__) : "f"(dep1), "f"(dep2) : "memory");   \
+      g_sor_times[((tid >> 5) * 8 + (T - 40)) * 16 + (slot)] = t__;                           \
+    }                                                                                         \
+  } while (0)
+#else
+#define SOR_STAMP(slot, dep1, dep2) do { } while (0)
+#endif
+
 struct SorSet {
   float4 A[4], B[4];     // records of the block (B unused for stereo)
   float4 own_u, own_v;   // previous-sweep du / dv of the block
   float4 bot_u, bot_v;   // sweep 0: previous du / dv of the row below
-  float2 wf[4];          // last sweep of the last inner iteration: flow of the block
 };
 
 template <int NOP, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
-    sor_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int f0, int K, int hpad, int write_flow) {
+    sor_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int f0, int K, int hpad) {
   extern __shared__ float4 s_pub[];  // [2][K][h+2][NF]
   constexpr int NF = (NOP == 2) ? 3 : 2;   // float4 per board entry: du x4, (dv x4), sv x4
   constexpr int RF = (NOP == 2) ? 2 : 1;   // float4 per pixel record
   const int fr = blockIdx.x, frame = f0 + fr;
   const int w = g.w, h = g.h;
   const int tid = threadIdx.x;
+  // ---- helper warp: the last warp of the CTA only warms L1 -------------------------------------
+  // Sweep 0 is the first toucher of every record / (du,dv) line; an L1-missing warp-level load
+  // takes ~75 cycles to issue against ~17 for a hit, which made the sweep-0 warps 2x slower than
+  // the others and set the pace of every super-step.  One extra warp touches the lines PD
+  // super-steps ahead (one 128-byte line per lane and instruction), so the compute warps only
+  // ever hit L1.
+  if (tid >= K * hpad) {
+    const int lane = tid & 31, W4h = (g.w + 3) >> 2;
+    constexpr int NQh = (NOP == 2) ? 8 : 4, PD = 3;
+    const int S_h = W4h + g.h + 2 * K - 2, dmax_h = W4h + g.h - 1, wps = hpad >> 5;
+    const float4* recb = pl.rec + (size_t)blockIdx.x * pl.rec_stride;
+    const float4* dudb = pl.dudv + (size_t)blockIdx.x * pl.dudv_stride;
+    for (int T = -PD; T < S_h; ++T) {
+      int d = T + PD;   // sweep 0's diagonal of super-step T+PD
+      d = d > dmax_h ? dmax_h : d;
+      // records: NQh rows of hpad float4 -> hpad*NQh/8 lines of 128 bytes
+      for (int ln = lane; ln < wps * 4 * NQh; ln += 32) {
+        float x;
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(x) : "l"(recb + (size_t)d * NQh * hpad + ln * 8));
+      }
+      // (du,dv) of diagonal d+1 (own values one step later, row-below values of this step)
+      const int d1 = d + 1 > dmax_h ? dmax_h : d + 1;
+      for (int ln = lane; ln < wps * 4 * 2; ln += 32) {
+        float x;
+        asm volatile("ld.global.f32 %0, [%1];" : "=f"(x) : "l"(dudb + (size_t)d1 * 2 * hpad + ln * 8));
+      }
+      if (T >= 0) __syncthreads();
+    }
+    return;
+  }
   const int k = tid / hpad, jraw = tid - k * hpad;
   const bool valid = jraw < h;
   const int j = valid ? jraw : h - 1;      // idle lanes shadow the last row, never store
@@ -416,49 +466,44 @@ __global__ void __launch_bounds__(MAXT, 1)
   const unsigned a_bot = sbase + (unsigned)((km * hb + j + 2) * NF) * 16u;
   const bool first_row = (j == 0), last_row = (j == h - 1);
   const bool k0 = (k == 0), klast = (k == K - 1);
-  const bool do_flow = klast && write_flow;
   const float omega = vp.omega;
 
   // skewed arrays: block (I, j) float4 q at ((I + j) * NQ + q) * hpad + j
   constexpr int NQ = 4 * RF;
-  const int jb = last_row ? j : j + 1;  // bottom row (clamped; unused on the last row)
-  const float4* const recp = pl.rec + (size_t)fr * pl.rec_stride + (size_t)j * NQ * hpad + j;
-  float4* const drow4 = pl.dudv + (size_t)fr * pl.dudv_stride + (size_t)j * 2 * hpad + j;
-  const float4* const dbot4 = pl.dudv + (size_t)fr * pl.dudv_stride + (size_t)jb * 2 * hpad + jb;
-  const int bstep_r = NQ * hpad, bstep_d = 2 * hpad;  // float4 per block step
-  float* const flow = g.flow + (size_t)frame * g.flow_frame_stride + (size_t)j * w * NOP;
+  const float4* const rec_f = pl.rec + (size_t)fr * pl.rec_stride + j;      // + (d*NQ + q)*hpad
+  float4* const dud_f = pl.dudv + (size_t)fr * pl.dudv_stride + j;         // + (d*2 + q)*hpad
+  const int jbo = (jraw + 1 < hpad) ? 1 : 0;  // lane offset of the row below (stay inside the row of lanes)
+  const int bstep_r = NQ * hpad, bstep_d = 2 * hpad;  // float4 per diagonal
+  (void)frame;
 
   const int W4 = (w + 3) >> 2;
   const int tstart = j + 2 * k;
   const int S = W4 + h + 2 * K - 2;  // super-steps 0 .. (W4-1)+(h-1)+2(K-1)
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  // loads block `blk` (clamped) into a parity set
-  auto load_set = [&](SorSet& s, int blk) {
-    const int nb = blk < 0 ? 0 : (blk > W4 - 1 ? W4 - 1 : blk);
-    const float4* rp = recp + nb * bstep_r;
+  // Loads the block this thread handles at super-step `Tn` into a parity set.  Addresses are
+  // formed from the DIAGONAL d = I + j = Tn - 2k, which is the same for all lanes of a warp, so
+  // every load instruction touches 512 contiguous bytes even when some lanes are out of range
+  // (clamping the block index per lane instead scatters those lanes over up to 32 lines per
+  // instruction and cost ~1200 cycles per super-step on sweep 0).  d is clamped uniformly; lanes
+  // whose block does not exist read garbage they never use.
+  const int dmax = W4 + h - 1;
+  auto load_set = [&](SorSet& s, int Tn) {
+    int d = Tn - 2 * k;
+    d = d < 0 ? 0 : (d > dmax ? dmax : d);
+    const float4* rp = rec_f + (size_t)d * bstep_r;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       s.A[c] = ldg128(rp + (c * RF) * hpad);
       if (NOP == 2) s.B[c] = ldg128(rp + (c * RF + 1) * hpad);
     }
     if (k0) {
-      // beyond the row end the right neighbour is 0 (solver.c:96-99): handled by has_r below,
-      // so the clamped load needs no masking here
-      s.own_u = ldg128_rw(drow4 + nb * bstep_d);
-      s.bot_u = ldg128_rw(dbot4 + nb * bstep_d);
+      const int d1 = d + 1 > dmax ? dmax : d + 1;   // row below: diagonal d+1, lane j+1
+      s.own_u = ldg128_rw(dud_f + (size_t)d * bstep_d);
+      s.bot_u = ldg128_rw(dud_f + (size_t)d1 * bstep_d + jbo);
       if (NOP == 2) {
-        s.own_v = ldg128_rw(drow4 + nb * bstep_d + hpad);
-        s.bot_v = ldg128_rw(dbot4 + nb * bstep_d + hpad);
-      }
-    }
-    if (do_flow) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        int col = 4 * nb + c;
-        col = col > w - 1 ? w - 1 : col;
-        if (NOP == 2) s.wf[c] = reinterpret_cast<const float2*>(flow)[col];
-        else s.wf[c].x = flow[col];
+        s.own_v = ldg128_rw(dud_f + (size_t)d * bstep_d + hpad);
+        s.bot_v = ldg128_rw(dud_f + (size_t)d1 * bstep_d + hpad + jbo);
       }
     }
   };
@@ -467,8 +512,9 @@ __global__ void __launch_bounds__(MAXT, 1)
   unsigned prevb = bufbytes, curb = 0;   // T even: write buffer 0, read buffer 1
 
   // one super-step: `cur` holds block I, `nxt` block I+1
-  auto step = [&](SorSet& cur, SorSet& nxt, int I) {
+  auto step = [&](SorSet& cur, SorSet& nxt, int I, int T) {
     const bool in_range = valid & (I >= 0) & (I < W4);
+    SOR_STAMP(0, omega, omega);
     if (!k0) {  // previous-sweep values come from the board (written one super-step ago)
       nxt.own_u = lds128(a_right + prevb);
       cur.bot_u = lds128(a_bot + prevb);
@@ -480,6 +526,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     const float4 top_u = lds128(a_top + prevb);
     const float4 top_v = (NOP == 2) ? lds128(a_top + prevb + 16) : z4;
     const float4 top_s = lds128(a_top + prevb + (NF - 1) * 16);
+    SOR_STAMP(1, top_s.w, top_u.x);
     const float ou[5] = {cur.own_u.x, cur.own_u.y, cur.own_u.z, cur.own_u.w, nxt.own_u.x};
     const float ov[5] = {cur.own_v.x, cur.own_v.y, cur.own_v.z, cur.own_v.w, nxt.own_v.x};
     const float tu[4] = {top_u.x, top_u.y, top_u.z, top_u.w};
@@ -509,6 +556,7 @@ __global__ void __launch_bounds__(MAXT, 1)
       // the block's records are needed no further except a11,a12,a22,sh: keep those, refill the
       // set for super-step T+2 now, so the loads fly while the recurrence below keeps the
       // pipeline latency-bound anyway
+      SOR_STAMP(2, s1[3], s2[3]);
       float ca11[4], ca12[4], ca22[4], chh[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -517,13 +565,8 @@ __global__ void __launch_bounds__(MAXT, 1)
         ca22[c] = cur.A[c].z;
         chh[c] = cur.B[c].y;
       }
-      float wfx[4], wfy[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        wfx[c] = cur.wf[c].x;
-        wfy[c] = cur.wf[c].y;
-      }
-      load_set(cur, I + 2);
+      load_set(cur, T + 2);
+      SOR_STAMP(3, s1[0], s2[0]);
       // ... then the sequential recurrence along the row (solver.c:206-210)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -536,11 +579,7 @@ __global__ void __launch_bounds__(MAXT, 1)
         nu[c] = du_l;
         nv[c] = dv_l;
       }
-      if (klast && in_range && write_flow) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (col0 + c < w) reinterpret_cast<float2*>(flow)[col0 + c] = make_float2(wfx[c] + nu[c], wfy[c] + nv[c]);
-      }
+      SOR_STAMP(4, nu[3], nv[3]);
     } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -564,24 +603,19 @@ __global__ void __launch_bounds__(MAXT, 1)
         nv[c] = 0.f;
         ns[c] = vv;
       }
-      if (klast && in_range && write_flow) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (col0 + c < w) {
-            const float tsum = cur.wf[c].x + nu[c];
-            flow[col0 + c] = (g.camlr == 0) ? (tsum < 0.0f ? tsum : 0.0f) : (tsum > 0.0f ? tsum : 0.0f);
-          }
-      }
-      load_set(cur, I + 2);
+      load_set(cur, T + 2);
     }
     sts128(a_me + curb, make_float4(nu[0], nu[1], nu[2], nu[3]));
     if (NOP == 2) sts128(a_me + curb + 16, make_float4(nv[0], nv[1], nv[2], nv[3]));
     sts128(a_me + curb + (NF - 1) * 16, make_float4(ns[0], ns[1], ns[2], ns[3]));
     if (klast && in_range) {
-      drow4[I * bstep_d] = make_float4(nu[0], nu[1], nu[2], nu[3]);
-      if (NOP == 2) drow4[I * bstep_d + hpad] = make_float4(nv[0], nv[1], nv[2], nv[3]);
+      float4* dst = dud_f + (size_t)(I + j) * bstep_d;
+      dst[0] = make_float4(nu[0], nu[1], nu[2], nu[3]);
+      if (NOP == 2) dst[hpad] = make_float4(nv[0], nv[1], nv[2], nv[3]);
     }
+    SOR_STAMP(5, nu[0], nu[1]);
     __syncthreads();
+    SOR_STAMP(6, omega, omega);
     const unsigned tmp = prevb;
     prevb = curb;
     curb = tmp;
@@ -593,15 +627,34 @@ __global__ void __launch_bounds__(MAXT, 1)
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     s0.B[c] = s1.B[c] = z4;
-    s0.wf[c] = s1.wf[c] = make_float2(0.f, 0.f);
   }
-  load_set(s0, -tstart);      // block of super-step 0
-  load_set(s1, 1 - tstart);   // block of super-step 1
+  load_set(s0, 0);   // super-step 0
+  load_set(s1, 1);   // super-step 1
   int I = -tstart;
 #pragma unroll 1
   for (int T = 0; T < S; T += 2, I += 2) {
-    step(s0, s1, I);
-    if (T + 1 < S) step(s1, s0, I + 1);
+    step(s0, s1, I, T);
+    if (T + 1 < S) step(s1, s0, I + 1, T + 1);
+  }
+}
+
+// K12 at the end of the level: flow = w + dw (refine_variational.cpp:210-221; stereo clamp
+// :299-314).  Kept out of the SOR kernel: the flow array is row-major per frame, so reading it
+// from one-thread-per-row SOR lanes costs 32 cache lines per load instruction.
+template <int NOP>
+__global__ void __launch_bounds__(256) flow_update_kernel(LevelGeom g, VarRefPlanes pl, int f0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int fr = blockIdx.z, frame = f0 + fr;
+  if (i >= g.w || j >= g.h) return;
+  const float* dudv = reinterpret_cast<const float*>(pl.dudv + (size_t)fr * pl.dudv_stride);
+  const size_t b = skew_f4(i >> 2, j, 0, 2, pl.hpad) * 4 + (i & 3);
+  float* f = g.flow + (size_t)frame * g.flow_frame_stride + ((size_t)j * g.w + i) * NOP;
+  if (NOP == 2) {
+    const float2 wv = *reinterpret_cast<const float2*>(f);
+    *reinterpret_cast<float2*>(f) = make_float2(wv.x + dudv[b], wv.y + dudv[b + 4 * pl.hpad]);
+  } else {
+    const float t = f[0] + dudv[b];
+    f[0] = (g.camlr == 0) ? (t < 0.0f ? t : 0.0f) : (t > 0.0f ? t : 0.0f);
   }
 }
 
@@ -626,9 +679,9 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   // registers per thread); otherwise one sweep per launch, 1024-thread variant for tall levels.
   const int K = vp.n_solver;
   const int hpad = ((g.h + 31) / 32) * 32;
-  const bool fused = (K >= 1) && (K * hpad <= 512);
+  const bool fused = (K >= 1) && (K * hpad + 32 <= 512);
   const int kl = fused ? K : 1;
-  const int nthreads = kl * hpad;
+  const int nthreads = kl * hpad + 32;  // + one helper (L1 prefetch) warp
   const int nf4 = (NOP == 2) ? 3 : 2;
   const size_t smem = sizeof(float4) * 2 * kl * (g.h + 2) * nf4;
   // register budget follows the CTA size: <=256 threads -> up to 255 registers (no reuse of
@@ -645,19 +698,28 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
       assemble_kernel<C, NOP><<<grid, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
     }
     ++launches;
-    const int last = (it == vp.n_inner - 1) ? 1 : 0;
     const int nl = fused ? 1 : K;
     for (int s = 0; s < nl; ++s) {
-      const int wf = (last && s == nl - 1) ? 1 : 0;
       ProfScope scope(prof, KC_VR_SOR);
-      if (variant == 0) sor_kernel<NOP, 256><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad, wf);
-      else if (variant == 1) sor_kernel<NOP, 512><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad, wf);
-      else sor_kernel<NOP, 1024><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad, wf);
+      if (variant == 0) sor_kernel<NOP, 256><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad);
+      else if (variant == 1) sor_kernel<NOP, 512><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad);
+      else sor_kernel<NOP, 1024><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad);
       ++launches;
     }
   }
+  if (vp.n_inner > 0) {
+    ProfScope scope(prof, KC_VR_SETUP);
+    flow_update_kernel<NOP><<<grid, block, 0, st>>>(g, pl, f0);
+    ++launches;
+  }
   return cudaGetLastError() == cudaSuccess ? launches : -1;
 }
+
+#ifdef OFDIS_SOR_TIMING
+extern "C" int ofdis_debug_sor_times(long long* dst) {
+  return cudaMemcpyFromSymbol(dst, g_sor_times, sizeof(g_sor_times)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int launch_varref(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
                   cudaStream_t st, Profiler* prof) {
