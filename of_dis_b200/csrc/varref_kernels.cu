@@ -382,6 +382,8 @@ __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+#include "sor_tma_kernel.cuh"
+
 // Thread layout: tid = k*hpad + j with hpad a multiple of 32, so the sweep index k (and with
 // it the "sweep 0 reads global / last sweep writes global" roles) is uniform per warp.
 // Out-of-range super-steps execute the same straight-line code on clamped addresses and
@@ -692,12 +694,25 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
     else if (variant == 1) cudaFuncSetAttribute(sor_kernel<NOP, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     else cudaFuncSetAttribute(sor_kernel<NOP, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
+  // TMA-producer variant when all sweeps fit one CTA of <= 288 threads and the stage ring fits
+  // shared memory (the common case: level heights up to 85 rows with 3 sweeps)
+  const int tma_threads = K * hpad + 32;
+  const size_t tma_smem = (size_t)sor_tma_stages(K) * (4 * (NOP == 2 ? 2 : 1) + 2) * hpad * 16 +
+                          sizeof(float4) * 2 * (size_t)K * (g.h + 2) * nf4 + 8 * (size_t)sor_tma_stages(K);
+  const bool use_tma = (K >= 1) && tma_threads <= 288 && tma_smem <= 200 * 1024;
+  if (use_tma) cudaFuncSetAttribute(sor_tma_kernel<NOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem);
   for (int it = 0; it < vp.n_inner; ++it) {
     {
       ProfScope scope(prof, KC_VR_ASSEMBLE);
       assemble_kernel<C, NOP><<<grid, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
     }
     ++launches;
+    if (use_tma) {
+      ProfScope scope(prof, KC_VR_SOR);
+      sor_tma_kernel<NOP><<<nf, tma_threads, tma_smem, st>>>(g, pl, vp, K, hpad);
+      ++launches;
+      continue;
+    }
     const int nl = fused ? 1 : K;
     for (int s = 0; s < nl; ++s) {
       ProfScope scope(prof, KC_VR_SOR);
