@@ -225,7 +225,7 @@ class Context:
         li = self.level_info(level)
         pitch = (li["w"] + 3) // 4 * 4
         C = self.prm.noc
-        per = {"mask": 1, "dudv": 2, "rec": 8 if self.prm.nop == 2 else 4}.get(name, C)
+        per = {"mask": 1, "dudv": 2, "rec": 8 if self.prm.nop == 2 else 5}.get(name, C)
         buf = np.empty(pitch * li["h"] * per, np.float32)
         n = lib().ofdis_debug_get(self._h, name.encode(), frame, _ptr(buf), buf.size)
         if n < 0:

@@ -350,7 +350,7 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   pl.hpad = ((L->h + 31) / 32) * 32;
   {
     const size_t diag = (size_t)((L->w + 3) / 4 + L->h + 2) * pl.hpad;
-    pl.rec_stride = diag * (L->nop == 2 ? 8 : 4);
+    pl.rec_stride = diag * (L->nop == 2 ? 8 : 5);
     pl.dudv_stride = diag * 2;
   }
   const int n = launch_varref(*L, pl, vp, f0, f1, ctx->stream, ctx->prof);
@@ -472,8 +472,8 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
     // stored skewed (see VarRefPlanes); returned in natural (h, pitch, per-pixel) order
     const bool is_rec = name[0] == 'r';
     const int hpad = ((L->h + 31) / 32) * 32, W4 = (L->w + 3) / 4;
-    const int nq = is_rec ? (L->nop == 2 ? 8 : 4) : 2;            // float4 per 4-pixel block
-    const int per = is_rec ? (L->nop == 2 ? 8 : 4) : 2;           // floats per pixel
+    const int nq = is_rec ? (L->nop == 2 ? 8 : 5) : 2;            // float4 (fields) per 4-pixel block
+    const int per = is_rec ? (L->nop == 2 ? 8 : 5) : 2;           // floats per pixel
     const size_t stride = (size_t)(W4 + L->h + 2) * hpad * nq;    // float4 per frame
     if (plane * per > max_floats) return OFDIS_ERR_ARG;
     std::vector<float> raw(stride * 4);
@@ -483,10 +483,9 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
     for (int j = 0; j < L->h; ++j)
       for (int i = 0; i < L->w; ++i)
         for (int e = 0; e < per; ++e) {
-          // rec: pixel c owns floats c*per..; dudv: float4 0 = du x4, float4 1 = dv x4
-          const int fl = is_rec ? (i & 3) * per + e : e * 4 + (i & 3);
-          const size_t f4 = skew_f4(i >> 2, j, fl / 4, nq, hpad);
-          dst[((size_t)j * L->pitch + i) * per + e] = raw[f4 * 4 + (fl & 3)];
+          // both are SoA inside the block: float4 e holds field e of the block's 4 pixels
+          const size_t f4 = skew_f4(i >> 2, j, e, nq, hpad);
+          dst[((size_t)j * L->pitch + i) * per + e] = raw[f4 * 4 + (i & 3)];
         }
     return (long)(plane * per);
   }

@@ -12,8 +12,9 @@
 //     shared-memory stages, PF super-steps ahead of sweep 0;
 //   * a diagonal stays resident while sweeps 0..K-1 consume it (super-steps n .. n+2(K-1)), so
 //     the records are fetched from L2 once instead of K times;
-//   * compute warps wait on the stage's mbarrier (complete long before, in steady state) and read
-//     their own 16-byte columns with conflict-free LDS.128.
+//   * the producer also observes completion (mbarrier wait one super-step ahead of use) so the
+//     compute warps just read their own 16-byte columns with conflict-free LDS.128 after the
+//     CTA barrier.
 // Stage reuse needs no "empty" barriers: the per-super-step __syncthreads orders the consumers'
 // last read of a stage before the producer's next copy into it (plus a proxy fence).
 #pragma once
@@ -42,7 +43,78 @@ __device__ __forceinline__ float lds32(unsigned addr) {
   return v;
 }
 
-constexpr int SOR_TMA_PF = 2;  // producer lead (super-steps)
+
+// ---------------------------------------------------------------------------
+// One 4-pixel block of the lexicographic SOR, shared by both kernel variants.
+// F: record fields of the block (flow: a11^-1 a12^-1 a22^-1 b1 b2 sh sv sv_top; stereo: A11 b1 sh
+// sv sv_top), one float4 per field.  own_*: previous-sweep values of the block, rf_*: previous-sweep
+// value of the first column of the next block, top_*: this sweep's values of the row above,
+// bot_*: previous-sweep values of the row below.  du_l/dv_l/hl carry the left neighbour and its sh.
+// The expressions are the reference's (solver.c:204-210 middle, :122-123 first, :259-260 last line;
+// stereo :438-462); row-class and border cases select between both candidate values.
+__device__ __forceinline__ float f4c(const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
+
+template <int NOP>
+__device__ __forceinline__ void sor_block_update(const float4* F, const float4& own_u, const float4& own_v,
+                                                 float rf_u, float rf_v, const float4& top_u, const float4& top_v,
+                                                 const float4& bot_u, const float4& bot_v, bool first_row,
+                                                 bool last_row, int col0, int w, float omega, float& du_l,
+                                                 float& dv_l, float& hl, float* nu, float* nv) {
+  const float ou[5] = {own_u.x, own_u.y, own_u.z, own_u.w, rf_u};
+  const float ov[5] = {own_v.x, own_v.y, own_v.z, own_v.w, rf_v};
+  if (NOP == 2) {
+    // everything that does not depend on the left neighbour first (ILP) ...
+    float s1[4], s2[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool has_r = (col0 + c + 1 < w);
+      const float du_r = has_r ? ou[c + 1] : 0.0f, dv_r = has_r ? ov[c + 1] : 0.0f;
+      const float b1 = f4c(F[3], c), b2 = f4c(F[4], c), hh = f4c(F[5], c), vv = f4c(F[6], c), vt = f4c(F[7], c);
+      const float t1u = hh * du_r, t1v = hh * dv_r;
+      const float t2u = t1u + vt * f4c(top_u, c), t2v = t1v + vt * f4c(top_v, c);
+      const float bsu = first_row ? t1u : t2u, bsv = first_row ? t1v : t2v;
+      const float t3u = bsu + vv * f4c(bot_u, c), t3v = bsv + vv * f4c(bot_v, c);
+      s1[c] = (last_row ? bsu : t3u) + b1;
+      s2[c] = (last_row ? bsv : t3v) + b2;
+    }
+    // ... then the sequential recurrence along the row
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float a11 = f4c(F[0], c), a12 = f4c(F[1], c), a22 = f4c(F[2], c);
+      const float B1w = hl * du_l + s1[c], B2w = hl * dv_l + s2[c];
+      const bool has_l = (col0 + c > 0);
+      const float B1 = has_l ? B1w : s1[c], B2 = has_l ? B2w : s2[c];
+      du_l = ou[c] + omega * (a11 * B1 + a12 * B2 - ou[c]);
+      dv_l = ov[c] + omega * (a12 * B1 + a22 * B2 - ov[c]);
+      hl = f4c(F[5], c);
+      nu[c] = du_l;
+      nv[c] = dv_l;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int col = col0 + c;
+      const float du_r = ou[c + 1];
+      const float A11 = f4c(F[0], c), b1 = f4c(F[1], c), hh = f4c(F[2], c), vv = f4c(F[3], c), vt = f4c(F[4], c);
+      float sg = 0.0f;  // sigma accumulates top, left, bottom, right
+      const float s_t = sg - vt * f4c(top_u, c);
+      sg = first_row ? sg : s_t;
+      const float s_l = sg - hl * du_l;
+      sg = (col > 0) ? s_l : sg;
+      const float s_b = sg - vv * f4c(bot_u, c);
+      sg = last_row ? sg : s_b;
+      const float s_r = sg - hh * du_r;
+      sg = (col < w - 1) ? s_r : sg;
+      const float B1 = b1 - sg;
+      du_l = (1.0f - omega) * ou[c] + omega * (B1 / A11);
+      hl = hh;
+      nu[c] = du_l;
+      nv[c] = 0.f;
+    }
+  }
+}
+
+constexpr int SOR_TMA_PF = 3;  // producer lead (super-steps)
 // ring depth: diagonal n is read by sweep k at super-step n+2k, and its (du,dv) part by sweep 0 at
 // super-step n+1; it may be overwritten PF super-steps before its successor is first needed
 __host__ __device__ inline int sor_tma_stages(int K) { return 2 * K + SOR_TMA_PF; }
@@ -51,9 +123,8 @@ template <int NOP>
 __global__ void __launch_bounds__(288, 1)
     sor_tma_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int K, int hpad) {
   extern __shared__ __align__(128) float4 s_dyn[];
-  constexpr int NF = (NOP == 2) ? 3 : 2;  // board entry: du x4, (dv x4), sv x4
-  constexpr int RF = (NOP == 2) ? 2 : 1;
-  constexpr int NQ = 4 * RF;              // record float4 per block
+  constexpr int NF = (NOP == 2) ? 2 : 1;  // board entry: du x4, (dv x4)
+  constexpr int NQ = (NOP == 2) ? 8 : 5;  // record fields (float4) per block
   constexpr int PF = SOR_TMA_PF;
   const int NR = sor_tma_stages(K);
   const int fr = blockIdx.x;
@@ -92,12 +163,22 @@ __global__ void __launch_bounds__(288, 1)
     };
     if (lead)
       for (int n = 0; n < PF && n < S; ++n) issue(n);
+    // Completion is observed by the producer, not by the consumers: before the barrier that ends
+    // super-step T-1 the producer waits until load T has landed (it was issued PF-1 super-steps
+    // earlier), so after that barrier every compute warp may read loads <= T without touching an
+    // mbarrier (a try_wait on a completed phase still cost ~260 cycles per warp and super-step).
+    mbar_wait(mbar0, 0);  // load 0, needed by sweep 0 in super-step 0
+    __syncthreads();
     for (int T = 0; T < S; ++T) {
       if (lead && T + PF < S) {
         // the consumers' reads of this stage (generic proxy) were ordered by the barrier that
         // ended super-step T-1; order them before the async-proxy write
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         issue(T + PF);
+      }
+      if (T + 1 < S) {
+        const int m = T + 1;
+        mbar_wait(mbar0 + 8u * (unsigned)(m % NR), (unsigned)((m / NR) & 1));
       }
       __syncthreads();
     }
@@ -124,20 +205,19 @@ __global__ void __launch_bounds__(288, 1)
   float4 own_u = z4, own_v = z4;  // sweeps > 0: previous-sweep values of the current block
   unsigned prevb = bufbytes, curb = 0;
   int I = -tstart;
+  __syncthreads();  // load 0 has landed (producer waited for it)
 #pragma unroll 1
   for (int T = 0; T < S; ++T, ++I) {
     const bool in_range = valid & (I >= 0) & (I < W4);
+    SOR_STAMP(0, omega, omega);
     const int n = T - 2 * k;  // load number == diagonal of this warp's blocks
     const int nn = n < 0 ? 0 : n;
     const unsigned st = (unsigned)(nn % NR);
-    if (n >= 0) mbar_wait(mbar0 + 8u * st, (unsigned)((nn / NR) & 1));
+    SOR_STAMP(1, omega, omega);
     const unsigned sa = sbase + st * stage_bytes;
-    float4 A[4], B[4];
+    float4 F[NQ];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      A[c] = lds128(sa + (c * RF) * rowb + lane_off);
-      B[c] = (NOP == 2) ? lds128(sa + (c * RF + 1) * rowb + lane_off) : z4;
-    }
+    for (int f = 0; f < NQ; ++f) F[f] = lds128(sa + f * rowb + lane_off);
     float4 bot_u, bot_v = z4, nxt_u = z4, nxt_v = z4;
     float rf_u, rf_v = 0.f;
     if (k0) {
@@ -170,73 +250,14 @@ __global__ void __launch_bounds__(288, 1)
     }
     const float4 top_u = lds128(a_top + prevb);
     const float4 top_v = (NOP == 2) ? lds128(a_top + prevb + 16) : z4;
-    const float4 top_s = lds128(a_top + prevb + (NF - 1) * 16);
-    const float ou[5] = {own_u.x, own_u.y, own_u.z, own_u.w, rf_u};
-    const float ov[5] = {own_v.x, own_v.y, own_v.z, own_v.w, rf_v};
-    const float tu[4] = {top_u.x, top_u.y, top_u.z, top_u.w};
-    const float tv[4] = {top_v.x, top_v.y, top_v.z, top_v.w};
-    const float ts[4] = {top_s.x, top_s.y, top_s.z, top_s.w};
-    const float bu[4] = {bot_u.x, bot_u.y, bot_u.z, bot_u.w};
-    const float bv[4] = {bot_v.x, bot_v.y, bot_v.z, bot_v.w};
-    float nu[4], nv[4], ns[4];
+    SOR_STAMP(2, top_u.w, F[NQ - 1].x);
+    float nu[4], nv[4];
     const int col0 = 4 * I;
-    if (NOP == 2) {
-      // everything that does not depend on the left neighbour first (ILP) ...
-      float s1[4], s2[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const bool has_r = (col0 + c + 1 < w);
-        const float du_r = has_r ? ou[c + 1] : 0.0f, dv_r = has_r ? ov[c + 1] : 0.0f;
-        const float b1 = A[c].w, b2 = B[c].x, hh = B[c].y, vv = B[c].z;
-        // solver.c:204-205 (middle lines), :122-123 (first line), :259-260 (last line)
-        const float t1u = hh * du_r, t1v = hh * dv_r;
-        const float t2u = t1u + ts[c] * tu[c], t2v = t1v + ts[c] * tv[c];
-        const float bsu = first_row ? t1u : t2u, bsv = first_row ? t1v : t2v;
-        const float t3u = bsu + vv * bu[c], t3v = bsv + vv * bv[c];
-        s1[c] = (last_row ? bsu : t3u) + b1;
-        s2[c] = (last_row ? bsv : t3v) + b2;
-        ns[c] = vv;
-      }
-      // ... then the sequential recurrence along the row (solver.c:206-210)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float a11 = A[c].x, a12 = A[c].y, a22 = A[c].z;
-        const float B1w = hl * du_l + s1[c], B2w = hl * dv_l + s2[c];
-        const bool has_l = (col0 + c > 0);
-        const float B1 = has_l ? B1w : s1[c], B2 = has_l ? B2w : s2[c];
-        du_l = ou[c] + omega * (a11 * B1 + a12 * B2 - ou[c]);
-        dv_l = ov[c] + omega * (a12 * B1 + a22 * B2 - ov[c]);
-        hl = B[c].y;
-        nu[c] = du_l;
-        nv[c] = dv_l;
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int col = col0 + c;
-        const float du_r = ou[c + 1];
-        const float A11 = A[c].x, b1 = A[c].y, hh = A[c].z, vv = A[c].w;
-        // solver.c:438-462: sigma accumulates top, left, bottom, right
-        float sg = 0.0f;
-        const float s_t = sg - ts[c] * tu[c];
-        sg = first_row ? sg : s_t;
-        const float s_l = sg - hl * du_l;
-        sg = (col > 0) ? s_l : sg;
-        const float s_b = sg - vv * bu[c];
-        sg = last_row ? sg : s_b;
-        const float s_r = sg - hh * du_r;
-        sg = (col < w - 1) ? s_r : sg;
-        const float B1 = b1 - sg;
-        du_l = (1.0f - omega) * ou[c] + omega * (B1 / A11);
-        hl = hh;
-        nu[c] = du_l;
-        nv[c] = 0.f;
-        ns[c] = vv;
-      }
-    }
+    sor_block_update<NOP>(F, own_u, own_v, rf_u, rf_v, top_u, top_v, bot_u, bot_v, first_row, last_row, col0, w,
+                          omega, du_l, dv_l, hl, nu, nv);
+    SOR_STAMP(4, nu[3], nv[3]);
     sts128(a_me + curb, make_float4(nu[0], nu[1], nu[2], nu[3]));
     if (NOP == 2) sts128(a_me + curb + 16, make_float4(nv[0], nv[1], nv[2], nv[3]));
-    sts128(a_me + curb + (NF - 1) * 16, make_float4(ns[0], ns[1], ns[2], ns[3]));
     if (klast && in_range) {  // coalesced: lanes of a warp share the diagonal
       float4* dst = dud_g + (size_t)(I + j) * 2 * hpad + j;
       dst[0] = make_float4(nu[0], nu[1], nu[2], nu[3]);
@@ -246,7 +267,9 @@ __global__ void __launch_bounds__(288, 1)
       own_u = nxt_u;
       own_v = nxt_v;
     }
+    SOR_STAMP(5, nu[0], nu[1]);
     __syncthreads();
+    SOR_STAMP(6, omega, omega);
     const unsigned tmp = prevb;
     prevb = curb;
     curb = tmp;

@@ -19,6 +19,21 @@ namespace ofdis {
 
 namespace {
 
+#ifdef OFDIS_SOR_TIMING
+// debug build only: per-warp cycle stamps of a few super-steps of frame 0 (tools/sor_timing.py)
+__device__ long long g_sor_times[64 * 8 * 16];
+#define SOR_STAMP(slot, dep1, dep2)                                                           \
+  do {                                                                                        \
+    if (fr == 0 && (tid & 31) == 0 && T >= 40 && T < 48) {                                    \
+      long long t__;                                                                          \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t__) : "f"(dep1), "f"(dep2) : "memory");   \
+      g_sor_times[((tid >> 5) * 8 + (T - 40)) * 16 + (slot)] = t__;                           \
+    }                                                                                         \
+  } while (0)
+#else
+#define SOR_STAMP(slot, dep1, dep2) do { } while (0)
+#endif
+
 #define DATANORM (0.1f * 0.1f)       /* opticalflow_aux.c:10 */
 #define EPS_COLOR (0.001f * 0.001f)  /* :11 */
 #define EPS_GRAD (0.001f * 0.001f)   /* :12 */
@@ -322,9 +337,18 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     else dps = hl + hh + vt + vv;
     const float iA11 = A22 + dps, iA22 = A11 + dps;
     const float det = iA11 * iA22 - A12 * A12;
-    float4* rec = pl.rec + (size_t)fr * pl.rec_stride;
-    rec[skew_f4(i >> 2, j, (i & 3) * 2, 8, hpad)] = make_float4(iA11 / det, A12 / -det, iA22 / det, B1);
-    rec[skew_f4(i >> 2, j, (i & 3) * 2 + 1, 8, hpad)] = make_float4(B2, hh, vv, 0.0f);
+    // record of the 4-pixel block, SoA: float4 f of the block holds field f of its 4 pixels;
+    // fields: a11^-1, a12^-1, a22^-1, b1, b2, sh, sv, sv(row above)
+    float* rec = reinterpret_cast<float*>(pl.rec + (size_t)fr * pl.rec_stride);
+    const size_t b0 = skew_f4(i >> 2, j, 0, 8, hpad) * 4 + (i & 3), fs = (size_t)hpad * 4;
+    rec[b0] = iA11 / det;
+    rec[b0 + fs] = A12 / -det;
+    rec[b0 + 2 * fs] = iA22 / det;
+    rec[b0 + 3 * fs] = B1;
+    rec[b0 + 4 * fs] = B2;
+    rec[b0 + 5 * fs] = hh;
+    rec[b0 + 6 * fs] = vv;
+    rec[b0 + 7 * fs] = vt;
   } else {
     // sor_coupled_slow_but_readable_DE (solver.c:438-460): A11 = a11 + sum_dpsis (top,left,bottom,right)
     float sum = 0.0f;
@@ -332,7 +356,14 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     if (i > 0) sum += hl;
     if (j < h - 1) sum += vv;
     if (i < w - 1) sum += hh;
-    pl.rec[(size_t)fr * pl.rec_stride + skew_f4(i >> 2, j, i & 3, 4, hpad)] = make_float4(A11 + sum, B1, hh, vv);
+    // stereo record fields: A11 = a11 + sum, b1, sh, sv, sv(row above)
+    float* rec = reinterpret_cast<float*>(pl.rec + (size_t)fr * pl.rec_stride);
+    const size_t b0 = skew_f4(i >> 2, j, 0, 5, hpad) * 4 + (i & 3), fs = (size_t)hpad * 4;
+    rec[b0] = A11 + sum;
+    rec[b0 + fs] = B1;
+    rec[b0 + 2 * fs] = hh;
+    rec[b0 + 3 * fs] = vv;
+    rec[b0 + 4 * fs] = vt;
   }
 }
 
@@ -395,23 +426,8 @@ __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
 // for the final write the flow) sits in set[T&1], loaded at the end of super-step T-2
 // straight into its final registers (prefetch distance 2, no copies).  The other set holds
 // block I+1, whose first column is the right neighbour of this block's last column.
-#ifdef OFDIS_SOR_TIMING
-// debug build only: per-warp cycle stamps of a few super-steps of frame 0 (tools/sor_timing.py)
-__device__ long long g_sor_times[64 * 8 * 16];
-#define SOR_STAMP(slot, dep1, dep2)                                                           \
-  do {                                                                                        \
-    if (fr == 0 && (tid & 31) == 0 && T >= 40 && T < 48) {                                    \
-      long long t__;                                                                          \
-      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t__) : "f"(dep1), "f"(dep2) : "memory");   \
-      g_sor_times[((tid >> 5) * 8 + (T - 40)) * 16 + (slot)] = t__;                           \
-    }                                                                                         \
-  } while (0)
-#else
-#define SOR_STAMP(slot, dep1, dep2) do { } while (0)
-#endif
-
 struct SorSet {
-  float4 A[4], B[4];     // records of the block (B unused for stereo)
+  float4 F[8];           // record fields of the block (5 used for stereo)
   float4 own_u, own_v;   // previous-sweep du / dv of the block
   float4 bot_u, bot_v;   // sweep 0: previous du / dv of the row below
 };
@@ -420,8 +436,7 @@ template <int NOP, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
     sor_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int f0, int K, int hpad) {
   extern __shared__ float4 s_pub[];  // [2][K][h+2][NF]
-  constexpr int NF = (NOP == 2) ? 3 : 2;   // float4 per board entry: du x4, (dv x4), sv x4
-  constexpr int RF = (NOP == 2) ? 2 : 1;   // float4 per pixel record
+  constexpr int NF = (NOP == 2) ? 2 : 1;   // float4 per board entry: du x4, (dv x4)
   const int fr = blockIdx.x, frame = f0 + fr;
   const int w = g.w, h = g.h;
   const int tid = threadIdx.x;
@@ -433,7 +448,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   // ever hit L1.
   if (tid >= K * hpad) {
     const int lane = tid & 31, W4h = (g.w + 3) >> 2;
-    constexpr int NQh = (NOP == 2) ? 8 : 4, PD = 3;
+    constexpr int NQh = (NOP == 2) ? 8 : 5, PD = 3;
     const int S_h = W4h + g.h + 2 * K - 2, dmax_h = W4h + g.h - 1, wps = hpad >> 5;
     const float4* recb = pl.rec + (size_t)blockIdx.x * pl.rec_stride;
     const float4* dudb = pl.dudv + (size_t)blockIdx.x * pl.dudv_stride;
@@ -471,7 +486,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   const float omega = vp.omega;
 
   // skewed arrays: block (I, j) float4 q at ((I + j) * NQ + q) * hpad + j
-  constexpr int NQ = 4 * RF;
+  constexpr int NQ = (NOP == 2) ? 8 : 5;   // record fields (float4) per block
   const float4* const rec_f = pl.rec + (size_t)fr * pl.rec_stride + j;      // + (d*NQ + q)*hpad
   float4* const dud_f = pl.dudv + (size_t)fr * pl.dudv_stride + j;         // + (d*2 + q)*hpad
   const int jbo = (jraw + 1 < hpad) ? 1 : 0;  // lane offset of the row below (stay inside the row of lanes)
@@ -495,10 +510,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     d = d < 0 ? 0 : (d > dmax ? dmax : d);
     const float4* rp = rec_f + (size_t)d * bstep_r;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      s.A[c] = ldg128(rp + (c * RF) * hpad);
-      if (NOP == 2) s.B[c] = ldg128(rp + (c * RF + 1) * hpad);
-    }
+    for (int f = 0; f < NQ; ++f) s.F[f] = ldg128(rp + f * hpad);
     if (k0) {
       const int d1 = d + 1 > dmax ? dmax : d + 1;   // row below: diagonal d+1, lane j+1
       s.own_u = ldg128_rw(dud_f + (size_t)d * bstep_d);
@@ -527,89 +539,21 @@ __global__ void __launch_bounds__(MAXT, 1)
     }
     const float4 top_u = lds128(a_top + prevb);
     const float4 top_v = (NOP == 2) ? lds128(a_top + prevb + 16) : z4;
-    const float4 top_s = lds128(a_top + prevb + (NF - 1) * 16);
-    SOR_STAMP(1, top_s.w, top_u.x);
-    const float ou[5] = {cur.own_u.x, cur.own_u.y, cur.own_u.z, cur.own_u.w, nxt.own_u.x};
-    const float ov[5] = {cur.own_v.x, cur.own_v.y, cur.own_v.z, cur.own_v.w, nxt.own_v.x};
-    const float tu[4] = {top_u.x, top_u.y, top_u.z, top_u.w};
-    const float tv[4] = {top_v.x, top_v.y, top_v.z, top_v.w};
-    const float ts[4] = {top_s.x, top_s.y, top_s.z, top_s.w};
-    const float bu[4] = {cur.bot_u.x, cur.bot_u.y, cur.bot_u.z, cur.bot_u.w};
-    const float bv[4] = {cur.bot_v.x, cur.bot_v.y, cur.bot_v.z, cur.bot_v.w};
-    float nu[4], nv[4], ns[4];
+    float nu[4], nv[4];
     const int col0 = 4 * I;
-    if (NOP == 2) {
-      // everything that does not depend on the left neighbour first (ILP) ...
-      float s1[4], s2[4];
+    {
+      // the block's records are needed no further once copied: refill the set for super-step
+      // T+2 now, so the loads fly while the recurrence keeps the pipeline latency-bound anyway
+      float4 Fc[NQ];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const bool has_r = (col0 + c + 1 < w);
-        const float du_r = has_r ? ou[c + 1] : 0.0f, dv_r = has_r ? ov[c + 1] : 0.0f;
-        const float b1 = cur.A[c].w, b2 = cur.B[c].x, hh = cur.B[c].y, vv = cur.B[c].z;
-        // solver.c:204-205 (middle lines), :122-123 (first line), :259-260 (last line)
-        const float t1u = hh * du_r, t1v = hh * dv_r;
-        const float t2u = t1u + ts[c] * tu[c], t2v = t1v + ts[c] * tv[c];
-        const float bsu = first_row ? t1u : t2u, bsv = first_row ? t1v : t2v;
-        const float t3u = bsu + vv * bu[c], t3v = bsv + vv * bv[c];
-        s1[c] = (last_row ? bsu : t3u) + b1;
-        s2[c] = (last_row ? bsv : t3v) + b2;
-        ns[c] = vv;
-      }
-      // the block's records are needed no further except a11,a12,a22,sh: keep those, refill the
-      // set for super-step T+2 now, so the loads fly while the recurrence below keeps the
-      // pipeline latency-bound anyway
-      SOR_STAMP(2, s1[3], s2[3]);
-      float ca11[4], ca12[4], ca22[4], chh[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        ca11[c] = cur.A[c].x;
-        ca12[c] = cur.A[c].y;
-        ca22[c] = cur.A[c].z;
-        chh[c] = cur.B[c].y;
-      }
+      for (int f = 0; f < NQ; ++f) Fc[f] = cur.F[f];
+      const float4 ownu = cur.own_u, ownv = cur.own_v, botu = cur.bot_u, botv = cur.bot_v;
       load_set(cur, T + 2);
-      SOR_STAMP(3, s1[0], s2[0]);
-      // ... then the sequential recurrence along the row (solver.c:206-210)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float B1w = hl * du_l + s1[c], B2w = hl * dv_l + s2[c];
-        const bool has_l = (col0 + c > 0);
-        const float B1 = has_l ? B1w : s1[c], B2 = has_l ? B2w : s2[c];
-        du_l = ou[c] + omega * (ca11[c] * B1 + ca12[c] * B2 - ou[c]);
-        dv_l = ov[c] + omega * (ca12[c] * B1 + ca22[c] * B2 - ov[c]);
-        hl = chh[c];
-        nu[c] = du_l;
-        nv[c] = dv_l;
-      }
-      SOR_STAMP(4, nu[3], nv[3]);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int col = col0 + c;
-        const float du_r = ou[c + 1];
-        const float A11 = cur.A[c].x, b1 = cur.A[c].y, hh = cur.A[c].z, vv = cur.A[c].w;
-        // solver.c:438-462: sigma accumulates top, left, bottom, right
-        float sg = 0.0f;
-        const float s_t = sg - ts[c] * tu[c];
-        sg = first_row ? sg : s_t;
-        const float s_l = sg - hl * du_l;
-        sg = (col > 0) ? s_l : sg;
-        const float s_b = sg - vv * bu[c];
-        sg = last_row ? sg : s_b;
-        const float s_r = sg - hh * du_r;
-        sg = (col < w - 1) ? s_r : sg;
-        const float B1 = b1 - sg;
-        du_l = (1.0f - omega) * ou[c] + omega * (B1 / A11);
-        hl = hh;
-        nu[c] = du_l;
-        nv[c] = 0.f;
-        ns[c] = vv;
-      }
-      load_set(cur, T + 2);
+      sor_block_update<NOP>(Fc, ownu, ownv, nxt.own_u.x, nxt.own_v.x, top_u, top_v, botu, botv, first_row, last_row,
+                            col0, w, omega, du_l, dv_l, hl, nu, nv);
     }
     sts128(a_me + curb, make_float4(nu[0], nu[1], nu[2], nu[3]));
     if (NOP == 2) sts128(a_me + curb + 16, make_float4(nv[0], nv[1], nv[2], nv[3]));
-    sts128(a_me + curb + (NF - 1) * 16, make_float4(ns[0], ns[1], ns[2], ns[3]));
     if (klast && in_range) {
       float4* dst = dud_f + (size_t)(I + j) * bstep_d;
       dst[0] = make_float4(nu[0], nu[1], nu[2], nu[3]);
@@ -628,7 +572,6 @@ __global__ void __launch_bounds__(MAXT, 1)
   s1.own_u = s1.own_v = s1.bot_u = s1.bot_v = z4;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    s0.B[c] = s1.B[c] = z4;
   }
   load_set(s0, 0);   // super-step 0
   load_set(s1, 1);   // super-step 1
@@ -684,7 +627,7 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   const bool fused = (K >= 1) && (K * hpad + 32 <= 512);
   const int kl = fused ? K : 1;
   const int nthreads = kl * hpad + 32;  // + one helper (L1 prefetch) warp
-  const int nf4 = (NOP == 2) ? 3 : 2;
+  const int nf4 = (NOP == 2) ? 2 : 1;
   const size_t smem = sizeof(float4) * 2 * kl * (g.h + 2) * nf4;
   // register budget follows the CTA size: <=256 threads -> up to 255 registers (no reuse of
   // in-flight load destinations), <=512 -> 128, else 64 (spills; only for very tall levels)
@@ -697,7 +640,7 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   // TMA-producer variant when all sweeps fit one CTA of <= 288 threads and the stage ring fits
   // shared memory (the common case: level heights up to 85 rows with 3 sweeps)
   const int tma_threads = K * hpad + 32;
-  const size_t tma_smem = (size_t)sor_tma_stages(K) * (4 * (NOP == 2 ? 2 : 1) + 2) * hpad * 16 +
+  const size_t tma_smem = (size_t)sor_tma_stages(K) * ((NOP == 2 ? 8 : 5) + 2) * hpad * 16 +
                           sizeof(float4) * 2 * (size_t)K * (g.h + 2) * nf4 + 8 * (size_t)sor_tma_stages(K);
   const bool use_tma = (K >= 1) && tma_threads <= 288 && tma_smem <= 200 * 1024;
   if (use_tma) cudaFuncSetAttribute(sor_tma_kernel<NOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem);

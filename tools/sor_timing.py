@@ -17,7 +17,7 @@ ctx.sync()
 buf = np.zeros(64 * 8 * 16, np.int64)
 assert api.lib().ofdis_debug_sor_times(buf.ctypes.data_as(ctypes.c_void_p)) == 0
 t = buf.reshape(64, 8, 16)[:6, :, :7]   # last launch = level 3 (6 warps), steps 40..47
-names = ["start", "lds", "prep", "ldissue", "chain", "stores", "barrier"]
+names = ["start", "mbarwait", "lds", "prep", "chain", "stores", "barrier"]
 for wp in range(6):
     d = np.diff(t[wp], axis=1)          # per-step phase durations
     nxt = t[wp, 1:, 0] - t[wp, :-1, 6]  # barrier exit -> next start
