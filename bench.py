@@ -5,8 +5,10 @@
 
 A "step" is one pass of the hot path (all pyramid levels: patch inverse search,
 densification, variational refinement == the reference's "O.Flow Run-Time"
-region, oflow.cpp:113-114,355-360) over B pairs per GPU.  Pixels are counted at
-the ORIGINAL image size, once per pair.
+region, oflow.cpp:113-114,355-360) over B pairs per GPU (default 64 = the batch
+of BASELINE configs[3]; one pair alone leaves 147 of 148 SMs idle, see
+batch_sweep in the output).  Pixels are counted at the ORIGINAL image size, once
+per pair.
 
   value : device-timed, padded pyramids already resident in HBM
   e2e   : same metric through the C-ABI with pinned HOST buffers; H2D of the
@@ -173,7 +175,8 @@ def run_reference_arm(args, rank, world):
 
 def workload_config(args, world):
     return {"workload": "%d x (1024x436 gray pair, op-point 2: P=8 ov=0.4 levels 5..3, 12 GN iters, TV 3 SOR sweeps) "
-                        "per GPU = BASELINE configs[3] shard on configs[1] geometry" % args.batch,
+                        "per GPU per step (BASELINE configs[3]'s batch of 64 pairs of configs[1] geometry; "
+                        "single-pair and 8-pair latencies in batch_sweep)" % args.batch,
             "pairs_per_gpu": args.batch, "pairs_total": args.batch * world, "parallelism": "frames x%d" % world,
             "l2": "flushed between timed steps (256 MiB write)"}
 
@@ -183,7 +186,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=8, help="pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=64, help="pairs per GPU per step")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
@@ -313,6 +316,30 @@ def main():
         roof = {"bound": "hbm", "achieved": None, "peak": peaks()[0], "unit": "GB/s", "frac": None, "traffic": None,
                 "error": str(e)}
 
+    # ---- latency-bound small batches (configs[1] = one pair; configs[3]'s per-GPU shard = 8) ----
+    sweep = {}
+    if world == 1:
+        for b in (1, 8):
+            if b >= B:
+                continue
+            c2 = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, b, device=local,
+                             stream=stream.cuda_stream)
+            c2.upload_packed(0, b, host_in.data_ptr())
+            c2.set_graph_mode(True)
+            for _ in range(3):
+                c2.run(b)
+            ms = timed(lambda: c2.run(b), 10)
+
+            def e2e_b():
+                c2.upload_packed(0, b, host_in.data_ptr())
+                c2.run(b)
+                c2.get_flow_batch(0, b, host_out.data_ptr())
+
+            ms2 = timed(e2e_b, 10)
+            sweep[str(b)] = {"ms_per_step": ms, "value": b * H_ORG * W_ORG / (ms * 1e-3) / 1e6,
+                             "e2e_ms_per_step": ms2, "e2e_value": b * H_ORG * W_ORG / (ms2 * 1e-3) / 1e6}
+            c2.close()
+
     cores = os.cpu_count() or 1
     threads = min(cores, B)
     cpu_val, kind, done = cpu_reference_mpix(prm, pyrs, args.cpu_seconds, threads) if world == 1 else (None, None, 0)
@@ -324,7 +351,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
                 "h2d_bytes_per_step": int(B * ff * 4), "d2h_bytes_per_step": int(B * flow_floats * 4)},
         "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
-        "clocks": clocks, "roofline": roof,
+        "clocks": clocks, "roofline": roof, "batch_sweep": sweep,
     }
     if cpu_val is not None:
         line["cpu_baseline"] = {"value": cpu_val, "unit": "Mpix/s", "cores": threads, "kind": kind,
