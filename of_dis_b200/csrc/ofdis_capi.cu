@@ -15,6 +15,14 @@
 
 using namespace ofdis;
 
+// rows of the skewed SOR arrays: padded to 32/64/128/256 (template sizes of sor_tma_kernel), a
+// multiple of 32 beyond
+static int sor_hpad(int h) {
+  for (int p = 32; p <= 256; p *= 2)
+    if (h <= p) return p;
+  return ((h + 31) / 32) * 32;
+}
+
 struct ofdis_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -213,7 +221,7 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
     const size_t plane = (size_t)Lf.pitch * Lf.h;
     const int C = prm->noc;
     // skewed SOR arrays: (W4 + h) diagonals x hpad rows, 8 (rec) + 2 (dudv) float4 per block
-    const size_t diag = (size_t)((Lf.w + 3) / 4 + Lf.h + 2) * (((Lf.h + 31) / 32) * 32);
+    const size_t diag = (size_t)((Lf.w + 3) / 4 + Lf.h + 2) * sor_hpad(Lf.h);
     const size_t per_frame = plane * (1 + C + 8 * C) + diag * 4 * (8 + 2);
     ok = dalloc((void**)&ctx->d_planes, sizeof(float) * per_frame * max_frames);
     if (ok) {
@@ -347,7 +355,7 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   vp.half_delta_over3 = ctx->prm.tv_delta * 0.5f / 3.0f;
   VarRefPlanes pl = ctx->planes;
   pl.plane = (size_t)L->pitch * L->h;
-  pl.hpad = ((L->h + 31) / 32) * 32;
+  pl.hpad = sor_hpad(L->h);
   {
     const size_t diag = (size_t)((L->w + 3) / 4 + L->h + 2) * pl.hpad;
     pl.rec_stride = diag * (L->nop == 2 ? 8 : 5);
@@ -471,7 +479,7 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
   if (!strcmp(name, "dudv") || !strcmp(name, "rec")) {
     // stored skewed (see VarRefPlanes); returned in natural (h, pitch, per-pixel) order
     const bool is_rec = name[0] == 'r';
-    const int hpad = ((L->h + 31) / 32) * 32, W4 = (L->w + 3) / 4;
+    const int hpad = sor_hpad(L->h), W4 = (L->w + 3) / 4;
     const int nq = is_rec ? (L->nop == 2 ? 8 : 5) : 2;            // float4 (fields) per 4-pixel block
     const int per = is_rec ? (L->nop == 2 ? 8 : 5) : 2;           // floats per pixel
     const size_t stride = (size_t)(W4 + L->h + 2) * hpad * nq;    // float4 per frame

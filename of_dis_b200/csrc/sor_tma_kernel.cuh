@@ -119,9 +119,12 @@ constexpr int SOR_TMA_PF = 3;  // producer lead (super-steps)
 // super-step n+1; it may be overwritten PF super-steps before its successor is first needed
 __host__ __device__ inline int sor_tma_stages(int K) { return 2 * K + SOR_TMA_PF; }
 
-template <int NOP>
+// HPAD (rows padded to 32/64/128/256) is a template parameter so that every shared-memory
+// address is `base + immediate`; stage indices advance incrementally (no modulo in the loop).
+template <int NOP, int HPAD>
 __global__ void __launch_bounds__(288, 1)
-    sor_tma_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int K, int hpad) {
+    sor_tma_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int K) {
+  constexpr int hpad = HPAD;
   extern __shared__ __align__(128) float4 s_dyn[];
   constexpr int NF = (NOP == 2) ? 2 : 1;  // board entry: du x4, (dv x4)
   constexpr int NQ = (NOP == 2) ? 8 : 5;  // record fields (float4) per block
@@ -153,13 +156,14 @@ __global__ void __launch_bounds__(288, 1)
   // ---- producer warp ------------------------------------------------------------------------
   if (tid >= K * hpad) {
     const bool lead = (tid == K * hpad);
+    unsigned ist = 0;  // stage of the next load to issue
     auto issue = [&](int n) {  // load n -> stage n % NR: records of diagonal n, (du,dv) of n+1
-      const unsigned st = (unsigned)(n % NR);
-      const unsigned dst = sbase + st * stage_bytes, mb = mbar0 + 8u * st;
+      const unsigned dst = sbase + ist * stage_bytes, mb = mbar0 + 8u * ist;
       const int d = n > dmax ? dmax : n, d1 = n + 1 > dmax ? dmax : n + 1;
       mbar_expect_tx(mb, rec_bytes + dud_bytes);
       bulk_g2s(dst, rec_g + (size_t)d * NQ * hpad, rec_bytes, mb);
       bulk_g2s(dst + rec_bytes, dud_g + (size_t)d1 * 2 * hpad, dud_bytes, mb);
+      ist = (ist + 1 == (unsigned)NR) ? 0u : ist + 1;
     };
     if (lead)
       for (int n = 0; n < PF && n < S; ++n) issue(n);
@@ -169,6 +173,8 @@ __global__ void __launch_bounds__(288, 1)
     // mbarrier (a try_wait on a completed phase still cost ~260 cycles per warp and super-step).
     mbar_wait(mbar0, 0);  // load 0, needed by sweep 0 in super-step 0
     __syncthreads();
+    unsigned wst = 1, wpar = 0;  // stage / phase parity of load T+1
+    if (NR == 1) { wst = 0; wpar = 1; }
     for (int T = 0; T < S; ++T) {
       if (lead && T + PF < S) {
         // the consumers' reads of this stage (generic proxy) were ordered by the barrier that
@@ -176,10 +182,8 @@ __global__ void __launch_bounds__(288, 1)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         issue(T + PF);
       }
-      if (T + 1 < S) {
-        const int m = T + 1;
-        mbar_wait(mbar0 + 8u * (unsigned)(m % NR), (unsigned)((m / NR) & 1));
-      }
+      if (T + 1 < S) mbar_wait(mbar0 + 8u * wst, wpar);
+      if (++wst == (unsigned)NR) { wst = 0; wpar ^= 1u; }
       __syncthreads();
     }
     return;
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(288, 1)
   float du_l = 0.f, dv_l = 0.f, hl = 0.f;
   float4 own_u = z4, own_v = z4;  // sweeps > 0: previous-sweep values of the current block
   unsigned prevb = bufbytes, curb = 0;
+  unsigned st = 0, stp = 0;  // stages of load max(n,0) and of load n-1
   int I = -tstart;
   __syncthreads();  // load 0 has landed (producer waited for it)
 #pragma unroll 1
@@ -211,8 +216,6 @@ __global__ void __launch_bounds__(288, 1)
     const bool in_range = valid & (I >= 0) & (I < W4);
     SOR_STAMP(0, omega, omega);
     const int n = T - 2 * k;  // load number == diagonal of this warp's blocks
-    const int nn = n < 0 ? 0 : n;
-    const unsigned st = (unsigned)(nn % NR);
     SOR_STAMP(1, omega, omega);
     const unsigned sa = sbase + st * stage_bytes;
     float4 F[NQ];
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(288, 1)
       // first column of the next block are on diagonal n+1, staged with load n
       const unsigned sn = sa + rec_bytes;
       if (n >= 1) {
-        const unsigned sp = sbase + (unsigned)((nn - 1) % NR) * stage_bytes + rec_bytes;
+        const unsigned sp = sbase + stp * stage_bytes + rec_bytes;
         own_u = lds128(sp + lane_off);
         if (NOP == 2) own_v = lds128(sp + rowb + lane_off);
       } else {  // diagonal 0 has no predecessor stage; its only block is (I=0, j=0)
@@ -273,5 +276,9 @@ __global__ void __launch_bounds__(288, 1)
     const unsigned tmp = prevb;
     prevb = curb;
     curb = tmp;
+    if (n >= 0) {  // advance to the stage of the next diagonal
+      stp = st;
+      st = (st + 1 == (unsigned)NR) ? 0u : st + 1;
+    }
   }
 }

@@ -623,7 +623,7 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   // sweeps per SOR launch: all of them when (sweeps x padded rows) fits a 512-thread CTA (128
   // registers per thread); otherwise one sweep per launch, 1024-thread variant for tall levels.
   const int K = vp.n_solver;
-  const int hpad = ((g.h + 31) / 32) * 32;
+  const int hpad = pl.hpad;  // rows padded to 32/64/128/256 (or a multiple of 32 beyond)
   const bool fused = (K >= 1) && (K * hpad + 32 <= 512);
   const int kl = fused ? K : 1;
   const int nthreads = kl * hpad + 32;  // + one helper (L1 prefetch) warp
@@ -642,8 +642,20 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   const int tma_threads = K * hpad + 32;
   const size_t tma_smem = (size_t)sor_tma_stages(K) * ((NOP == 2 ? 8 : 5) + 2) * hpad * 16 +
                           sizeof(float4) * 2 * (size_t)K * (g.h + 2) * nf4 + 8 * (size_t)sor_tma_stages(K);
-  const bool use_tma = (K >= 1) && tma_threads <= 288 && tma_smem <= 200 * 1024;
-  if (use_tma) cudaFuncSetAttribute(sor_tma_kernel<NOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem);
+  const bool use_tma = (K >= 1) && tma_threads <= 288 && tma_smem <= 200 * 1024 &&
+                       (hpad == 32 || hpad == 64 || hpad == 128 || hpad == 256);
+  auto launch_tma = [&]() {
+#define SOR_TMA_LAUNCH(HP)                                                                             \
+  do {                                                                                                 \
+    cudaFuncSetAttribute(sor_tma_kernel<NOP, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem); \
+    sor_tma_kernel<NOP, HP><<<nf, tma_threads, tma_smem, st>>>(g, pl, vp, K);                            \
+  } while (0)
+    if (hpad == 32) SOR_TMA_LAUNCH(32);
+    else if (hpad == 64) SOR_TMA_LAUNCH(64);
+    else if (hpad == 128) SOR_TMA_LAUNCH(128);
+    else SOR_TMA_LAUNCH(256);
+#undef SOR_TMA_LAUNCH
+  };
   for (int it = 0; it < vp.n_inner; ++it) {
     {
       ProfScope scope(prof, KC_VR_ASSEMBLE);
@@ -652,7 +664,7 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
     ++launches;
     if (use_tma) {
       ProfScope scope(prof, KC_VR_SOR);
-      sor_tma_kernel<NOP><<<nf, tma_threads, tma_smem, st>>>(g, pl, vp, K, hpad);
+      launch_tma();
       ++launches;
       continue;
     }
