@@ -284,6 +284,228 @@ __global__ void __launch_bounds__(256) patch_optimize_kernel(LevelGeom g, PatchP
   }
 }
 
+// ---------------------------------------------------------------------------
+// Specialisation for the common operating points 1/2 (P = 8, gray): the 8 lanes of a patch
+// are its 8 columns, the 8 strided elements of a lane are the 8 rows of that column, so the
+// template, its gradients and the residual live in 32 registers (no shared memory), and the
+// bilinear taps of a lane are just two image columns of 9 rows (18 loads per iteration instead
+// of 32, no per-element offsets).  Arithmetic and reduction order are those of the generic kernel.
+template <int NOP>
+__global__ void __launch_bounds__(256) patch_p8c1_kernel(LevelGeom g, PatchParams pp, int f0,
+                                                          int init_from_coarser) {
+  const int tid = threadIdx.x;
+  const int l8 = tid & 7;
+  const int frame = f0 + blockIdx.y;
+  const int ip = blockIdx.x * (blockDim.x >> 3) + (tid >> 3);
+  const bool valid = ip < g.np;
+  constexpr int P = 8;
+  const float fn = 64.0f;
+  const int tw = g.tmp_w;
+  const float* i0 = g.img[0] + (size_t)frame * g.img_frame_stride;
+  const float* i0x = g.img[1] + (size_t)frame * g.img_frame_stride;
+  const float* i0y = g.img[2] + (size_t)frame * g.img_frame_stride;
+  const float* i1 = g.img[3] + (size_t)frame * g.img_frame_stride;
+
+  const int ipc = valid ? ip : 0;
+  const int gx_i = ipc / g.noph, gy_i = ipc - gx_i * g.noph;
+  const int cxi = gx_i * g.steps + g.offw, cyi = gy_i * g.steps + g.offh;
+  const float refx = (float)cxi, refy = (float)cyi;
+
+  // K1: column l8 of the template and its gradients (patch.cpp:287-332)
+  float T[8], GX[8], GY[8], R[8];
+  {
+    const int base = (cxi + g.pad - P / 2 + l8) + (cyi + g.pad - P / 2) * tw;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      T[k] = i0[base + k * tw];
+      GX[k] = i0x[base + k * tw];
+      GY[k] = i0y[base + k * tw];
+      acc = (k == 0) ? T[k] : acc + T[k];
+      R[k] = 0.f;
+    }
+    if (pp.patnorm > 0) {
+      const float m = fold8(acc, 0.f, true, false) / fn;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) T[k] = T[k] - m;
+    }
+  }
+  // Hessian + Cholesky (patch.cpp:71-88)
+  float L00, L10 = 0.f, L11 = 0.f;
+  {
+    float axx = 0.f, axy = 0.f, ayy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float vxx = GX[k] * GX[k], vxy = GX[k] * GY[k], vyy = GY[k] * GY[k];
+      axx = (k == 0) ? vxx : axx + vxx;
+      axy = (k == 0) ? vxy : axy + vxy;
+      ayy = (k == 0) ? vyy : ayy + vyy;
+    }
+    float H00 = fold8(axx, 0.f, true, false);
+    if (NOP == 2) {
+      const float H01 = fold8(axy, 0.f, true, false);
+      float H11 = fold8(ayy, 0.f, true, false);
+      if (H00 * H11 - H01 * H01 == 0.f) {
+        H00 = (float)((double)H00 + 1e-10);
+        H11 = (float)((double)H11 + 1e-10);
+      }
+      L00 = H00; L10 = H01; L11 = H11;
+      if (H00 > 0.f) {
+        L00 = sqrtf(H00);
+        L10 = H01 / L00;
+        const float x = H11 - L10 * L10;
+        if (x > 0.f) L11 = sqrtf(x);
+      }
+    } else {
+      if (H00 == 0.f) H00 = (float)((double)H00 + 1e-10);
+      L00 = H00 > 0.f ? sqrtf(H00) : H00;
+    }
+  }
+  // K2 (patchgrid.cpp:195-211)
+  float pin0 = 0.f, pin1 = 0.f;
+  if (init_from_coarser && g.flow_prev != nullptr) {
+    const float* fp = g.flow_prev + (size_t)frame * g.flow_prev_frame_stride;
+    const int i = (cyi >> 1) * (g.w / 2) + (cxi >> 1);
+    if (NOP == 2) {
+      const float2 v = reinterpret_cast<const float2*>(fp)[i];
+      pin0 = v.x * 2.f;
+      pin1 = v.y * 2.f;
+    } else {
+      pin0 = fp[i] * 2.f;
+    }
+  }
+  // K3 (patch.cpp:119-212, 264-284)
+  float p0 = pin0, p1 = pin1, dp0 = 0.f, dp1 = 0.f;
+  float ptx = refx + p0, pty = (NOP == 2) ? refy + p1 : refy;
+  const float stx = ptx, sty = pty;
+  float dpsq_init = 1e-10f, mares = 1e5f, mares_old = 1e20f;
+  int cnt = 0, conv = 0;
+  bool wrote_w = false, finishing = false, active = valid;
+  if (active && (ptx < g.lb || pty < g.lb || ptx > g.ubw || pty > g.ubh)) {
+    conv = 1;
+    active = false;
+  }
+  while (__any_sync(FULL, active)) {
+    float b0 = 0.f, b1 = 0.f, sw = 0.f;
+    {
+      float V[8];
+      float acc = 0.f;
+      if (active) {
+        const int pcx = (int)ceilf(ptx + .00001f), pcy = (int)ceilf(pty + .00001f);
+        const int pfx = (int)floorf(ptx), pfy = (int)floorf(pty);
+        const float rx = ptx - (float)pfx, ry = pty - (float)pfy;
+        const float w0 = rx * ry, w1 = (1.f - rx) * ry, w2 = rx * (1.f - ry), w3 = (1.f - rx) * (1.f - ry);
+        // window rows pcy-5 .. pcy+3, columns (pcx-5+l8) and (pcx-4+l8): d/c above, b/a below
+        const float* q = i1 + (pcx + g.pad - P / 2 - 1 + l8) + (pcy + g.pad - P / 2 - 1) * tw;
+        float cl = __ldg(q), cr = __ldg(q + 1);  // row above: d, c
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          q += tw;
+          const float bl = __ldg(q), br = __ldg(q + 1);  // this row: b, a
+          V[k] = w0 * br + w1 * bl + w2 * cr + w3 * cl;
+          acc = (k == 0) ? V[k] : acc + V[k];
+          cl = bl;
+          cr = br;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) V[k] = 0.f;
+      }
+      float m = 0.f;
+      if (pp.patnorm > 0) m = fold8(acc, 0.f, true, false) / fn;
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float d = V[k];
+          if (pp.patnorm > 0) d = d - m;
+          float r, w;
+          if (pp.costfct == 0) {
+            r = d - T[k];
+            w = fabsf(r);
+          } else if (pp.costfct == 1) {
+            const float t = d - T[k];
+            r = copysignf(sqrtf(fabsf(t)), t);
+            w = fabsf(r);
+          } else if (pp.costfct == 2) {
+            const float t = d - T[k];
+            const float hh = sqrtf((sqrtf(1.0f + (t * t) / 25.0f) - 1.0f) * 50.0f);
+            r = copysignf(hh, t);
+            w = fabsf(r);
+          } else {
+            r = d;
+            w = 0.f;
+          }
+          R[k] = r;
+          const float vx = GX[k] * r, vy = GY[k] * r;
+          b0 = (k == 0) ? vx : b0 + vx;
+          b1 = (k == 0) ? vy : b1 + vy;
+          sw = (k == 0) ? w : sw + w;
+        }
+        wrote_w = (pp.costfct >= 0 && pp.costfct <= 2);
+      }
+    }
+    b0 = fold8(b0, 0.f, true, false);
+    if (NOP == 2) b1 = fold8(b1, 0.f, true, false);
+    sw = fold8(sw, 0.f, true, false);
+    if (active) {
+      if (finishing) {
+        active = false;
+      } else {
+        const float dpsq = (NOP == 2) ? dp0 * dp0 + dp1 * dp1 : dp0 * dp0;
+        if (cnt == 1) dpsq_init = dpsq;
+        mares_old = mares;
+        mares = sw / fn;
+        const bool go = (cnt < pp.max_iter) & (mares > pp.res_thresh) &
+                        ((cnt < pp.min_iter) | (dpsq / dpsq_init >= pp.dp_thresh_sq)) &
+                        ((cnt < pp.min_iter) | (mares / mares_old <= pp.dr_thresh));
+        if (!go) {
+          conv = 1;
+          active = false;
+        } else {
+          cnt++;
+          if (NOP == 2) {
+            const float y0 = b0 / L00;
+            const float y1 = (b1 - L10 * y0) / L11;
+            dp1 = y1 / L11;
+            dp0 = (y0 - L10 * dp1) / L00;
+            p0 = p0 - dp0;
+            p1 = p1 - dp1;
+            ptx = refx + p0;
+            pty = refy + p1;
+          } else {
+            dp0 = (b0 / L00) / L00;
+            p0 = p0 - dp0;
+            p0 = (g.camlr == 0) ? std_min(p0, 0.0f) : std_max(p0, 0.0f);
+            ptx = refx + p0;
+          }
+          const float ex = stx - ptx, ey = sty - pty;
+          if (sqrtf(ex * ex + ey * ey) > g.outlierthresh || ptx < g.lb || pty < g.lb || ptx > g.ubw ||
+              pty > g.ubh) {
+            p0 = pin0;
+            p1 = pin1;
+            ptx = refx + p0;
+            if (NOP == 2) pty = refy + p1;
+            conv = 1;
+            finishing = true;
+          }
+        }
+      }
+    }
+  }
+  if (valid) {
+    float* pw = g.pat_w + ((size_t)frame * g.np + ip) * 64;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pw[l8 + 8 * k] = wrote_w ? fabsf(R[k]) : 0.f;
+    if (l8 == 0) {
+      float* po = g.pat_p + ((size_t)frame * g.np + ip) * NOP;
+      po[0] = p0;
+      if (NOP == 2) po[1] = p1;
+      g.pat_conv[(size_t)frame * g.np + ip] = conv;
+      g.pat_cnt[(size_t)frame * g.np + ip] = cnt;
+    }
+  }
+}
+
 // K4: PatGridClass::AggregateFlowDense (patchgrid.cpp:213-275,377-394) as a
 // per-pixel gather.  The reference scatters patch by patch in ip = x*noph + y
 // order; visiting the covering patches of a pixel in ascending (x, y) grid order
@@ -348,6 +570,12 @@ __global__ void __launch_bounds__(256) densify_kernel(LevelGeom g, int f0) {
 int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int f1, bool init_from_coarser,
                           cudaStream_t st, Profiler* prof) {
   ProfScope scope(prof, KC_PATCH);
+  if (g.P == 8 && g.noc == 1) {  // register-resident specialisation (operating points 1 and 2)
+    const dim3 grid8((g.np + 31) / 32, f1 - f0);
+    if (g.nop == 2) patch_p8c1_kernel<2><<<grid8, 256, 0, st>>>(g, pp, f0, init_from_coarser ? 1 : 0);
+    else patch_p8c1_kernel<1><<<grid8, 256, 0, st>>>(g, pp, f0, init_from_coarser ? 1 : 0);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
   const int n = g.novals;
   const int NK = (n / 8) + (((n % 8) >= 4) ? 1 : 0);
   int threads = 256;
