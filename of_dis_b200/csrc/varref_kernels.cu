@@ -626,7 +626,8 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   const int hpad = pl.hpad;  // rows padded to 32/64/128/256 (or a multiple of 32 beyond)
   const bool fused = (K >= 1) && (K * hpad + 32 <= 512);
   const int kl = fused ? K : 1;
-  const int nthreads = kl * hpad + 32;  // + one helper (L1 prefetch) warp
+  // + one helper (L1 prefetch) warp unless that would exceed the 1024-thread CTA limit
+  const int nthreads = (kl * hpad + 32 <= 1024) ? kl * hpad + 32 : kl * hpad;
   const int nf4 = (NOP == 2) ? 2 : 1;
   const size_t smem = sizeof(float4) * 2 * kl * (g.h + 2) * nf4;
   // register budget follows the CTA size: <=256 threads -> up to 255 registers (no reuse of

@@ -188,3 +188,30 @@ def test_properties_at_full_size(api):
     full = preprocess.postprocess(a, prm.sc_l, pyr.padw, pyr.padh, pyr.width_org, pyr.height_org)
     epe = np.sqrt(((full - gt) ** 2).sum(-1)).mean()
     assert epe < 0.5, epe
+
+
+def test_tall_level_1024_rows_uses_the_one_thread_per_row_limit(api, oracle_port):
+    """Refinement level with exactly 1024 rows (the SOR kernel's one-thread-per-row ceiling, as in
+    BASELINE configs[4]'s level 1): narrow stereo pair so the oracle stays fast."""
+    prm = params.from_cli_numbers("2 1 8 8 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split(), noc=1, nop=1)
+    i0, i1, _ = synth.synthetic_pair(2048, 96, 1, seed=9, amp=3.0, stereo=True)
+    pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
+    ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    ctx.upload_pyramids(0, pyr)
+    ctx.run(1)
+    assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "run h=1024")
+    ctx.close()
+    with pytest.raises(api.OfdisError):  # one row more is rejected, not mis-computed
+        api.Context(prm, 96, 2112, 8, 1)
+
+
+def test_full_size_rgb_op3_l1_cost_vs_oracle(api, oracle_port):
+    """BASELINE configs[2]: run_OF_RGB geometry, 1920x1080, op-point-3 parameters with L1 cost."""
+    prm = params.from_cli_numbers("6 2 16 16 0.05 0.95 0 12 0.75 0 1 1 1 10 10 5 1 3 1.6 0".split(), noc=3)
+    i0, i1, _ = synth.synthetic_pair(1080, 1920, 3, seed=2)
+    pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
+    ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    ctx.upload_pyramids(0, pyr)
+    ctx.run(1)
+    assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "cfg3 run")
+    ctx.close()
