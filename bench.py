@@ -178,7 +178,7 @@ def workload_config(args, world):
                         "per GPU per step (BASELINE configs[3]'s batch of 64 pairs of configs[1] geometry; "
                         "single-pair and 8-pair latencies in batch_sweep)" % args.batch,
             "pairs_per_gpu": args.batch, "pairs_total": args.batch * world, "parallelism": "frames x%d" % world,
-            "lanes": "2 contexts/streams per GPU, consecutive steps overlap",
+            "lanes": "%d contexts/streams per GPU, consecutive steps overlap" % max(1, args.lanes),
             "l2": "two alternating working sets of ~2 MB per pair exceed the 126 MB L2 at the default batch; "
                   "single_lane and batch_sweep numbers are taken with L2 flushed (256 MiB write) before every step"}
 
@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="pairs per GPU per step")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--lanes", type=int, default=4, help="contexts/streams whose steps overlap")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -252,11 +253,13 @@ def main():
     # Two lanes (context + stream each): step i runs on lane i%2, so consecutive steps overlap on the
     # device -- copies of one step under the kernels of the other, and the latency-bound refinement
     # kernels of two batches side by side (one batch of 64 pairs occupies 64 of 148 SMs there).
-    stream2 = torch.cuda.Stream()
-    ctx2 = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, B, device=local,
-                       stream=stream2.cuda_stream)
-    host_out2 = torch.empty((B, flow_floats), dtype=torch.float32).pin_memory()
-    lanes = ((ctx, stream, host_out), (ctx2, stream2, host_out2))
+    NL = max(1, args.lanes)
+    lanes = [(ctx, stream, host_out)]
+    for _ in range(NL - 1):
+        st_l = torch.cuda.Stream()
+        lanes.append((api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, B, device=local,
+                                  stream=st_l.cuda_stream), st_l,
+                      torch.empty((B, flow_floats), dtype=torch.float32).pin_memory()))
     for c, _, _ in lanes:
         c.upload_packed(0, B, host_in.data_ptr())
         c.set_graph_mode(True)
@@ -265,28 +268,30 @@ def main():
         """K steps alternating over the two lanes; device time from one event pair spanning both streams."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
-        stream2.wait_event(ev0)
+        for _, st_l, _ in lanes[1:]:
+            st_l.wait_event(ev0)
         for i in range(steps):
             step_fn(i)
-        stream.wait_stream(stream2)
+        for _, st_l, _ in lanes[1:]:
+            stream.wait_stream(st_l)
         ev1.record(stream)
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / steps
 
     # ---- device-resident throughput -----------------------------------------
     def resident_step(i):
-        lanes[i & 1][0].run(B)
+        lanes[i % NL][0].run(B)
 
-    for i in range(2 * args.warmup):
+    for i in range(NL * args.warmup):
         resident_step(i)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
-    l0 = ctx.launch_count + ctx2.launch_count
+    l0 = sum(c.launch_count for c, _, _ in lanes)
     t0 = time.time()
     ms_res = maxrank(pipelined(resident_step, args.steps))
-    launches = (ctx.launch_count + ctx2.launch_count - l0) // args.steps
+    launches = (sum(c.launch_count for c, _, _ in lanes) - l0) // args.steps
     barrier()
     # one lane alone, L2 flushed before every step (latency of one batch)
     ms_res_single = maxrank(timed(lambda: ctx.run(B), args.steps))
@@ -295,13 +300,19 @@ def main():
     # Every step copies its own inputs from pinned host memory and its flows back.  No L2 flush is
     # possible inside an overlapped region; the two alternating working sets (2 x ~2 MB per pair)
     # exceed L2 at the default batch.
+    # e2e transfers only I0,I1 of every level (the gradients of I0 are derived on the device by
+    # ofdis_upload_packed_images -- inside the timed region); that halves the PCIe bytes per pair
+    n_img = ctx.packed_images_frame_floats
+    host_img = torch.empty((B, n_img), dtype=torch.float32).pin_memory()
+    host_img.copy_(host_in[:, :n_img])
+
     def e2e_step(i):
-        c, _, ho = lanes[i & 1]
-        c.upload_packed(0, B, host_in.data_ptr())
+        c, _, ho = lanes[i % NL]
+        c.upload_packed_images(0, B, host_img.data_ptr())
         c.run(B)
         c.get_flow_batch(0, B, ho.data_ptr())
 
-    for i in range(2 * args.warmup):
+    for i in range(NL * args.warmup):
         e2e_step(i)
     barrier()
     w0 = time.perf_counter()
@@ -313,14 +324,15 @@ def main():
 
     # serial variant: one lane, H2D -> run -> D2H back to back, L2 flushed between steps
     def e2e_serial():
-        ctx.upload_packed(0, B, host_in.data_ptr())
+        ctx.upload_packed_images(0, B, host_img.data_ptr())
         ctx.run(B)
         ctx.get_flow_batch(0, B, host_out.data_ptr())
 
     for _ in range(args.warmup):
         e2e_serial()
     ms_e2e_serial = maxrank(timed(e2e_serial, args.steps))
-    ctx2.close()
+    for c, _, _ in lanes[1:]:
+        c.close()
 
     if rank != 0:
         ctx.close()
@@ -392,8 +404,8 @@ def main():
         "single_lane": {"ms_per_step": ms_res_single, "value": pix / (ms_res_single * 1e-3) / 1e6,
                         "note": "one context, one stream, L2 flushed before every step"},
         "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
-                "h2d_bytes_per_step": int(B * ff * 4), "d2h_bytes_per_step": int(B * flow_floats * 4),
-                "mode": "2 lanes (context+stream), step i on lane i%2: copies and kernels of consecutive steps overlap",
+                "h2d_bytes_per_step": int(B * n_img * 4), "d2h_bytes_per_step": int(B * flow_floats * 4),
+                "mode": "%d lanes (context+stream), step i on lane i %% lanes: copies and kernels of consecutive steps overlap" % NL,
                 "serial_ms_per_step": ms_e2e_serial,
                 "serial_value": pix / (ms_e2e_serial * 1e-3) / 1e6},
         "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),

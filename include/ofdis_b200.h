@@ -100,10 +100,18 @@ int ofdis_upload_level(ofdis_ctx* ctx, int frame, int level, const float* i0, co
                        const float* i0y, const float* i1, int memkind);
 
 /* Packed transfer: all levels sc_f..sc_l of frames [f0,f1) in the context's own
- * layout (per frame: for level = sc_f down to sc_l: I0, I0x, I0y, I1), one copy. */
+ * layout (per frame: I0,I1 of levels sc_f..sc_l, then I0x,I0y of the same levels; use
+ * ofdis_packed_offset), one copy. */
 size_t ofdis_packed_frame_floats(const ofdis_ctx* ctx);
 size_t ofdis_packed_offset(const ofdis_ctx* ctx, int level, int which /*0 I0,1 I0x,2 I0y,3 I1*/);
 int ofdis_upload_packed(ofdis_ctx* ctx, int f0, int f1, const float* packed, int memkind);
+
+/* Images-only transfer (extension): the leading ofdis_packed_images_frame_floats()
+ * floats of a packed frame are I0,I1 of all levels (offsets as ofdis_packed_offset reports them);
+ * `packed` holds only those, frame after frame.  One 2-D copy, then the gradients of I0 are derived
+ * on the device (Sobel 3x3 / 8, reflect101, zero border: run_dense.cpp:156-157,171-172). */
+size_t ofdis_packed_images_frame_floats(const ofdis_ctx* ctx);
+int ofdis_upload_packed_images(ofdis_ctx* ctx, int f0, int f1, const float* packed, int memkind);
 
 /* Stage operators on frames [f0,f1) of one level. */
 int ofdis_patgrid_optimize(ofdis_ctx* ctx, int level, int f0, int f1, int init_from_coarser);

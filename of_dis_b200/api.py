@@ -28,7 +28,7 @@ EXPORTS = [
     "ofdis_patgrid_optimize", "ofdis_patgrid_aggregate", "ofdis_varref_refine", "ofdis_run", "ofdis_sync",
     "ofdis_get_flow", "ofdis_set_flow", "ofdis_get_flow_batch", "ofdis_get_patches", "ofdis_debug_get",
     "ofdis_debug_varref_iters", "ofdis_launch_count", "ofdis_set_graph_mode", "ofdis_profile_run",
-    "ofdis_set_camlr", "ofdis_set_dp_thresh_sq",
+    "ofdis_set_camlr", "ofdis_set_dp_thresh_sq", "ofdis_packed_images_frame_floats", "ofdis_upload_packed_images",
 ]
 
 
@@ -49,6 +49,7 @@ def lib():
         L.ofdis_last_error.restype = ctypes.c_char_p
         L.ofdis_version.restype = ctypes.c_char_p
         L.ofdis_packed_frame_floats.restype = ctypes.c_size_t
+        L.ofdis_packed_images_frame_floats.restype = ctypes.c_size_t
         L.ofdis_packed_offset.restype = ctypes.c_size_t
         L.ofdis_debug_get.restype = ctypes.c_long
         L.ofdis_launch_count.restype = ctypes.c_long
@@ -60,6 +61,8 @@ def lib():
         L.ofdis_last_error.argtypes = [ctypes.c_void_p]
         L.ofdis_launch_count.argtypes = [ctypes.c_void_p]
         L.ofdis_packed_frame_floats.argtypes = [ctypes.c_void_p]
+        L.ofdis_packed_images_frame_floats.argtypes = [ctypes.c_void_p]
+        L.ofdis_upload_packed_images.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.ofdis_packed_offset.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.ofdis_upload_packed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.ofdis_upload_level.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int]
@@ -153,6 +156,14 @@ class Context:
     def upload_pyramids(self, frame: int, pyr):
         for lv in range(self.prm.sc_l, self.prm.sc_f + 1):
             self.upload_level(frame, lv, pyr.i0[lv], pyr.i0x[lv], pyr.i0y[lv], pyr.i1[lv])
+
+    @property
+    def packed_images_frame_floats(self) -> int:
+        return lib().ofdis_packed_images_frame_floats(self._h)
+
+    def upload_packed_images(self, f0, f1, packed, memkind=MEM_HOST):
+        """I0,I1 only (the leading part of the packed layout); gradients are derived on the device."""
+        self._ck(lib().ofdis_upload_packed_images(self._h, f0, f1, _ptr(packed), memkind))
 
     def upload_packed(self, f0, f1, packed, memkind=MEM_HOST):
         self._ck(lib().ofdis_upload_packed(self._h, f0, f1, _ptr(packed), memkind))

@@ -33,6 +33,7 @@ struct ofdis_ctx {
   std::vector<LevelGeom> lev;      // index: level - sc_l
   std::vector<size_t> img_off;     // [lev][4] offsets (floats) inside one packed frame
   size_t frame_floats = 0;
+  size_t images_floats = 0;        // leading part of a packed frame that holds I0,I1 of all levels
   float* d_img = nullptr;          // [max_frames][frame_floats]
   std::vector<float*> d_flow;      // index level - sc_l, plus one extra entry for level sc_f+1 (initflow)
   std::vector<size_t> flow_floats;
@@ -177,17 +178,23 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
   // geometry + packed image layout: per frame, level sc_f down to sc_l, I0 I0x I0y I1
   ctx->lev.resize(ctx->nlev);
   ctx->img_off.resize((size_t)ctx->nlev * 4);
+  // packed frame: [for level sc_f..sc_l: I0, I1] then [for level sc_f..sc_l: I0x, I0y].  The image
+  // block is contiguous so that ofdis_upload_packed_images can move it with one 2-D copy and derive
+  // the gradients on the device.
   size_t off = 0;
-  for (int sl = prm->sc_f; sl >= prm->sc_l; --sl) {
-    LevelGeom& L = ctx->lev[sl - prm->sc_l];
-    make_level(L, ctx, sl);
-    const size_t n = (size_t)L.tmp_w * L.tmp_h * L.noc;
-    for (int k = 0; k < 4; ++k) {
-      ctx->img_off[(size_t)(sl - prm->sc_l) * 4 + k] = off;
-      off += (n + 3) / 4 * 4;  // keep every array 16-byte aligned
+  for (int pass = 0; pass < 2; ++pass)
+    for (int sl = prm->sc_f; sl >= prm->sc_l; --sl) {
+      LevelGeom& L = ctx->lev[sl - prm->sc_l];
+      if (pass == 0) make_level(L, ctx, sl);
+      const size_t n = (size_t)L.tmp_w * L.tmp_h * L.noc;
+      const int which[2][2] = {{0, 3}, {1, 2}};  // pass 0: I0, I1; pass 1: I0x, I0y
+      for (int k = 0; k < 2; ++k) {
+        ctx->img_off[(size_t)(sl - prm->sc_l) * 4 + which[pass][k]] = off;
+        off += (n + 3) / 4 * 4;  // keep every array 16-byte aligned
+      }
     }
-  }
   ctx->frame_floats = off;
+  ctx->images_floats = ctx->img_off[(size_t)(prm->sc_f - prm->sc_l) * 4 + 1];  // first gradient array starts where the images end
 
   auto dalloc = [&](void** p, size_t bytes) -> bool {
     return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess;
@@ -204,8 +211,15 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
   }
   for (int li = 0; li < ctx->nlev && ok; ++li) {
     LevelGeom& L = ctx->lev[li];
-    for (int k = 0; k < 4; ++k) L.img[k] = ctx->d_img + ctx->img_off[(size_t)li * 4 + k];
-    L.img_frame_stride = ctx->frame_floats;
+    // device: block A = [frame][I0,I1 of all levels], block B = [frame][I0x,I0y of all levels]
+    const size_t gfl = ctx->frame_floats - ctx->images_floats;
+    float* blockB = ctx->d_img + ctx->images_floats * max_frames;
+    for (int k = 0; k < 4; ++k) {
+      const size_t o = ctx->img_off[(size_t)li * 4 + k];
+      const bool is_img = (k == 0 || k == 3);
+      L.img[k] = is_img ? ctx->d_img + o : blockB + (o - ctx->images_floats);
+      L.img_fs[k] = is_img ? ctx->images_floats : gfl;
+    }
     L.flow = ctx->d_flow[li];
     L.flow_frame_stride = ctx->flow_floats[li];
     L.flow_prev = ctx->d_flow[li + 1];
@@ -299,7 +313,7 @@ int ofdis_upload_level(ofdis_ctx* ctx, int frame, int level, const float* i0, co
   const size_t n = (size_t)L->tmp_w * L->tmp_h * L->noc;
   const float* src[4] = {i0, i0x, i0y, i1};
   for (int k = 0; k < 4; ++k)
-    CK(cudaMemcpyAsync(const_cast<float*>(L->img[k]) + (size_t)frame * ctx->frame_floats, src[k], sizeof(float) * n,
+    CK(cudaMemcpyAsync(const_cast<float*>(L->img[k]) + (size_t)frame * L->img_fs[k], src[k], sizeof(float) * n,
                        kind_in(memkind), ctx->stream));
   return OFDIS_OK;
 }
@@ -315,8 +329,30 @@ int ofdis_upload_packed(ofdis_ctx* ctx, int f0, int f1, const float* packed, int
   if (!ctx) return OFDIS_ERR_ARG;
   if (f0 < 0 || f1 > ctx->max_frames || f0 >= f1 || !packed) return fail(ctx, OFDIS_ERR_ARG, "upload_packed: bad argument");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpyAsync(ctx->d_img + (size_t)f0 * ctx->frame_floats, packed,
-                     sizeof(float) * ctx->frame_floats * (f1 - f0), kind_in(memkind), ctx->stream));
+  // host: [frame][images | gradients]; device: all images, then all gradients -> two 2-D copies
+  const size_t nif = ctx->images_floats, ngf = ctx->frame_floats - nif;
+  CK(cudaMemcpy2DAsync(ctx->d_img + (size_t)f0 * nif, sizeof(float) * nif, packed, sizeof(float) * ctx->frame_floats,
+                       sizeof(float) * nif, (size_t)(f1 - f0), kind_in(memkind), ctx->stream));
+  CK(cudaMemcpy2DAsync(ctx->d_img + nif * ctx->max_frames + (size_t)f0 * ngf, sizeof(float) * ngf, packed + nif,
+                       sizeof(float) * ctx->frame_floats, sizeof(float) * ngf, (size_t)(f1 - f0), kind_in(memkind),
+                       ctx->stream));
+  return OFDIS_OK;
+}
+
+size_t ofdis_packed_images_frame_floats(const ofdis_ctx* ctx) { return ctx ? ctx->images_floats : 0; }
+
+int ofdis_upload_packed_images(ofdis_ctx* ctx, int f0, int f1, const float* packed, int memkind) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  if (f0 < 0 || f1 > ctx->max_frames || f0 >= f1 || !packed) return fail(ctx, OFDIS_ERR_ARG, "upload_packed_images: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  // images of consecutive frames are contiguous on the device: one plain copy
+  CK(cudaMemcpyAsync(ctx->d_img + (size_t)f0 * ctx->images_floats, packed,
+                     sizeof(float) * ctx->images_floats * (f1 - f0), kind_in(memkind), ctx->stream));
+  for (int sl = ctx->prm.sc_f; sl >= ctx->prm.sc_l; --sl) {
+    const int n = launch_sobel(ctx->lev[sl - ctx->prm.sc_l], f0, f1, ctx->stream);
+    if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "sobel_kernel launch", cudaGetLastError());
+    ctx->launches += n;
+  }
   return OFDIS_OK;
 }
 

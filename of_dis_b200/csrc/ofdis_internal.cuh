@@ -18,7 +18,7 @@ struct LevelGeom {
   float lb, ubw, ubh, outlierthresh;
   // device pointers (frame 0); frame f adds f * stride
   const float* img[4];     // I0, I0x, I0y, I1 (padded, interleaved)
-  size_t img_frame_stride; // floats between consecutive frames in the packed image buffer
+  size_t img_fs[4];        // floats between consecutive frames of each array (images and gradients live in two blocks)
   float* flow;             // [frames][h][w][nop]
   size_t flow_frame_stride;
   const float* flow_prev;  // level+1 flow (or initflow), nullptr -> zero init
@@ -91,6 +91,7 @@ struct ProfScope {
 int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int f1, bool init_from_coarser,
                           cudaStream_t st, Profiler* prof = nullptr);
 int launch_densify(const LevelGeom& g, int f0, int f1, cudaStream_t st, Profiler* prof = nullptr);
+int launch_sobel(const LevelGeom& g, int f0, int f1, cudaStream_t st);
 int launch_varref(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
                   cudaStream_t st, Profiler* prof = nullptr);
 

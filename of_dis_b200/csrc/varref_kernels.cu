@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(256) warp_kernel(LevelGeom g, VarRefPlanes pl,
   const int o = j * g.pitch + i;
   pl.mask[(size_t)fr * pl.plane + o] =
       (xx >= 0 && xx <= g.w - 1 && yy >= 0 && yy <= g.h - 1) ? 1.0f : 0.0f;
-  const float* i1 = g.img[3] + (size_t)frame * g.img_frame_stride;
-  const float* i0 = g.img[0] + (size_t)frame * g.img_frame_stride;
+  const float* i1 = g.img[3] + (size_t)frame * g.img_fs[3];
+  const float* i0 = g.img[0] + (size_t)frame * g.img_fs[0];
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     const float s11 = i1[((y1 + g.pad) * g.tmp_w + x1 + g.pad) * C + c];

@@ -215,3 +215,27 @@ def test_full_size_rgb_op3_l1_cost_vs_oracle(api, oracle_port):
     ctx.run(1)
     assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "cfg3 run")
     ctx.close()
+
+
+@pytest.mark.parametrize("ch", [1, 3])
+def test_images_only_upload_derives_the_same_gradients_on_device(ch, api):
+    """ofdis_upload_packed_images (I0,I1 only; Sobel/8 on the device) == full upload, bit for bit."""
+    prm = params.from_cli_numbers("3 1 8 8 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split(), noc=ch)
+    nfr = 3
+    pyrs = []
+    for s in range(nfr):
+        i0, i1, _ = synth.synthetic_pair(120, 200, ch, seed=60 + s)  # odd level sizes: 15x25 at level 3
+        pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
+    ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, nfr)
+    full = np.stack([ctx.pack_frame(p) for p in pyrs])
+    ctx.upload_packed(0, nfr, full)
+    ctx.run(nfr)
+    ref = [ctx.get_flow(f, prm.sc_l) for f in range(nfr)]
+    ni = ctx.packed_images_frame_floats
+    assert 0 < ni < ctx.packed_frame_floats
+    ctx.upload_packed(0, nfr, np.zeros_like(full))          # wipe, then images only
+    ctx.upload_packed_images(0, nfr, np.ascontiguousarray(full[:, :ni]))
+    ctx.run(nfr)
+    for f in range(nfr):
+        assert_bits(ctx.get_flow(f, prm.sc_l), ref[f], "frame %d" % f)
+    ctx.close()
