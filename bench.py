@@ -191,7 +191,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="pairs per GPU per step")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--lanes", type=int, default=4, help="contexts/streams whose steps overlap")
+    ap.add_argument("--lanes", type=int, default=8, help="contexts/streams whose steps overlap")
+    ap.add_argument("--e2e-upload", choices=("images", "pyramids"), default="images",
+                    help="e2e H2D payload: I0,I1 of every level (gradients derived on the device) or all four arrays")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -204,9 +206,11 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from of_dis_b200 import api
+    from of_dis_b200 import api, numa
 
     torch.cuda.set_device(local)
+    # pinned staging buffers must live on the GPU's own socket (of_dis_b200/numa.py)
+    numa_node, prev_affinity = numa.bind_to_gpu_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
@@ -250,9 +254,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # Two lanes (context + stream each): step i runs on lane i%2, so consecutive steps overlap on the
-    # device -- copies of one step under the kernels of the other, and the latency-bound refinement
-    # kernels of two batches side by side (one batch of 64 pairs occupies 64 of 148 SMs there).
+    # NL lanes (context + stream each): step i runs on lane i % NL, so consecutive steps overlap on the
+    # device -- copies of one step under the kernels of the others, and the latency-bound refinement
+    # kernels of several batches side by side (one batch of 64 pairs occupies 64 of 148 SMs there).
     NL = max(1, args.lanes)
     lanes = [(ctx, stream, host_out)]
     for _ in range(NL - 1):
@@ -265,7 +269,7 @@ def main():
         c.set_graph_mode(True)
 
     def pipelined(step_fn, steps):
-        """K steps alternating over the two lanes; device time from one event pair spanning both streams."""
+        """K steps dealt round-robin to the lanes; device time from one event pair spanning all streams."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         for _, st_l, _ in lanes[1:]:
@@ -306,14 +310,28 @@ def main():
     host_img = torch.empty((B, n_img), dtype=torch.float32).pin_memory()
     host_img.copy_(host_in[:, :n_img])
 
+    images_only = args.e2e_upload == "images"
+
+    def upload(c, b=B):
+        if images_only:
+            c.upload_packed_images(0, b, host_img.data_ptr())
+        else:
+            c.upload_packed(0, b, host_in.data_ptr())
+
     def e2e_step(i):
         c, _, ho = lanes[i % NL]
-        c.upload_packed_images(0, B, host_img.data_ptr())
+        upload(c)
         c.run(B)
         c.get_flow_batch(0, B, ho.data_ptr())
 
-    for i in range(NL * args.warmup):
-        e2e_step(i)
+    # Warm-up: W steps per lane, continued until 0.4 s of copies have run -- an idle PCIe link takes
+    # ~0.2 s of traffic to leave its low-power state (tools/e2e_probe.py: first pass 30 GB/s, then 54).
+    n_warm_e2e, w_start = 0, time.perf_counter()
+    while n_warm_e2e < NL * args.warmup or time.perf_counter() - w_start < 0.4:
+        e2e_step(n_warm_e2e)
+        n_warm_e2e += 1
+        if n_warm_e2e % NL == 0:
+            torch.cuda.synchronize()
     barrier()
     w0 = time.perf_counter()
     ms_e2e = maxrank(pipelined(e2e_step, args.steps))
@@ -324,7 +342,7 @@ def main():
 
     # serial variant: one lane, H2D -> run -> D2H back to back, L2 flushed between steps
     def e2e_serial():
-        ctx.upload_packed_images(0, B, host_img.data_ptr())
+        upload(ctx)
         ctx.run(B)
         ctx.get_flow_batch(0, B, host_out.data_ptr())
 
@@ -360,7 +378,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("sor_dram_bytes_per_launch")
-        roof = {"bound": "hbm", "kernel": "sor_kernel (lexicographic SOR, all sweeps fused)", "achieved": ach,
+        roof = {"bound": "hbm", "kernel": "sor_tma_kernel (lexicographic SOR wavefront, all sweeps fused; sor_kernel on levels that exceed its shared-memory budget)", "achieved": ach,
                 "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": how,
                 "algorithmic_bytes_per_step": alg, "kernel_ms_per_step": sor["ms_per_step"],
                 "launches_per_step": sor["launches_per_step"],
@@ -384,7 +402,7 @@ def main():
             ms = timed(lambda: c2.run(b), 10)
 
             def e2e_b():
-                c2.upload_packed(0, b, host_in.data_ptr())
+                upload(c2, b)
                 c2.run(b)
                 c2.get_flow_batch(0, b, host_out.data_ptr())
 
@@ -393,6 +411,7 @@ def main():
                              "e2e_ms_per_step": ms2, "e2e_value": b * H_ORG * W_ORG / (ms2 * 1e-3) / 1e6}
             c2.close()
 
+    numa.unbind(prev_affinity)  # the CPU baseline uses every core of the host
     cores = os.cpu_count() or 1
     threads = min(cores, B)
     cpu_val, kind, done = cpu_reference_mpix(prm, pyrs, args.cpu_seconds, threads) if world == 1 else (None, None, 0)
@@ -404,7 +423,10 @@ def main():
         "single_lane": {"ms_per_step": ms_res_single, "value": pix / (ms_res_single * 1e-3) / 1e6,
                         "note": "one context, one stream, L2 flushed before every step"},
         "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
-                "h2d_bytes_per_step": int(B * n_img * 4), "d2h_bytes_per_step": int(B * flow_floats * 4),
+                "h2d_bytes_per_step": int(B * (n_img if images_only else ff) * 4),
+                "h2d_payload": "I0,I1 of levels %d..%d (I0x,I0y derived on the device inside the timed region)"
+                               % (prm.sc_f, prm.sc_l) if images_only else "I0,I0x,I0y,I1 of every level",
+                "host_numa_node": numa_node, "warmup_steps": n_warm_e2e, "d2h_bytes_per_step": int(B * flow_floats * 4),
                 "mode": "%d lanes (context+stream), step i on lane i %% lanes: copies and kernels of consecutive steps overlap" % NL,
                 "serial_ms_per_step": ms_e2e_serial,
                 "serial_value": pix / (ms_e2e_serial * 1e-3) / 1e6},
