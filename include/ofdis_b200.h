@@ -113,6 +113,29 @@ int ofdis_upload_packed(ofdis_ctx* ctx, int f0, int f1, const float* packed, int
 size_t ofdis_packed_images_frame_floats(const ofdis_ctx* ctx);
 int ofdis_upload_packed_images(ofdis_ctx* ctx, int f0, int f1, const float* packed, int memkind);
 
+/* Read-back of one padded array of the device pyramid (which: 0 I0, 1 I0x, 2 I0y, 3 I1); the
+ * inverse of ofdis_upload_level, used to check the device-built pyramids. */
+int ofdis_get_level(ofdis_ctx* ctx, int frame, int level, int which, float* dst, int memkind);
+
+/* Pyramid on the device (extension, SURVEY 8f rank 1 == ConstructImgPyramide, run_dense.cpp:130-178
+ * plus the divisibility padding of run_dense.cpp:298-311).
+ * ofdis_upload_frames_u8: `frames` = [frame][2][height_org][width_org][noc] 8-bit pixels (I0 then I1
+ *   of each pair); width_org/height_org must pad up to the context's width/height.  Builds levels
+ *   sc_l..sc_f of I0, I1 (box means), I0x, I0y (Sobel/8) and both paddings on the device.
+ * ofdis_upload_finest_level: `packed` = [frame][2][h][w][noc] float images of level sc_l WITHOUT
+ *   the border padding (h = height >> sc_l, ...; ofdis_finest_level_frame_floats() per frame);
+ *   coarser levels, gradients and paddings are derived on the device.  Smallest transfer that still
+ *   defines the run's input exactly. */
+int ofdis_upload_frames_u8(ofdis_ctx* ctx, int f0, int f1, const unsigned char* frames, int width_org, int height_org,
+                           int memkind);
+size_t ofdis_finest_level_frame_floats(const ofdis_ctx* ctx);
+int ofdis_upload_finest_level(ofdis_ctx* ctx, int f0, int f1, const float* packed, int memkind);
+
+/* Output stage on the device (extension, SURVEY 8f rank 2 == run_dense.cpp:407-414): flow of level
+ * sc_l times 2^sc_l, bilinear upsampling by 2^sc_l (half-pixel centres, edge clamped), crop of the
+ * divisibility padding.  `out` = [f1-f0][height_org][width_org][nop] floats. */
+int ofdis_get_flow_fullres(ofdis_ctx* ctx, int f0, int f1, float* out, int width_org, int height_org, int memkind);
+
 /* Stage operators on frames [f0,f1) of one level. */
 int ofdis_patgrid_optimize(ofdis_ctx* ctx, int level, int f0, int f1, int init_from_coarser);
 int ofdis_patgrid_aggregate(ofdis_ctx* ctx, int level, int f0, int f1);

@@ -29,6 +29,8 @@ EXPORTS = [
     "ofdis_get_flow", "ofdis_set_flow", "ofdis_get_flow_batch", "ofdis_get_patches", "ofdis_debug_get",
     "ofdis_debug_varref_iters", "ofdis_launch_count", "ofdis_set_graph_mode", "ofdis_profile_run",
     "ofdis_set_camlr", "ofdis_set_dp_thresh_sq", "ofdis_packed_images_frame_floats", "ofdis_upload_packed_images",
+    "ofdis_upload_frames_u8", "ofdis_finest_level_frame_floats", "ofdis_upload_finest_level", "ofdis_get_flow_fullres",
+    "ofdis_get_level",
 ]
 
 
@@ -64,6 +66,14 @@ def lib():
         L.ofdis_packed_images_frame_floats.argtypes = [ctypes.c_void_p]
         L.ofdis_upload_packed_images.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.ofdis_packed_offset.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.ofdis_get_level.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.ofdis_finest_level_frame_floats.restype = ctypes.c_size_t
+        L.ofdis_finest_level_frame_floats.argtypes = [ctypes.c_void_p]
+        L.ofdis_upload_finest_level.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.ofdis_upload_frames_u8.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int]
+        L.ofdis_get_flow_fullres.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int]
         L.ofdis_upload_packed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.ofdis_upload_level.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int]
         L.ofdis_level_info.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_IP] * 5
@@ -164,6 +174,29 @@ class Context:
     def upload_packed_images(self, f0, f1, packed, memkind=MEM_HOST):
         """I0,I1 only (the leading part of the packed layout); gradients are derived on the device."""
         self._ck(lib().ofdis_upload_packed_images(self._h, f0, f1, _ptr(packed), memkind))
+
+    def get_level(self, frame, level, which) -> np.ndarray:
+        """Padded device array `which` (0 I0, 1 I0x, 2 I0y, 3 I1) of one level."""
+        h, w = (self.height >> level) + 2 * self.pad, (self.width >> level) + 2 * self.pad
+        out = np.empty((h, w) if self.prm.noc == 1 else (h, w, self.prm.noc), np.float32)
+        self._ck(lib().ofdis_get_level(self._h, frame, level, which, _ptr(out), MEM_HOST))
+        return out
+
+    @property
+    def finest_level_frame_floats(self) -> int:
+        return lib().ofdis_finest_level_frame_floats(self._h)
+
+    def upload_finest_level(self, f0, f1, packed, memkind=MEM_HOST):
+        """[frame][2][h][w][noc] un-padded float images of level sc_l; the rest is derived on the device."""
+        self._ck(lib().ofdis_upload_finest_level(self._h, f0, f1, _ptr(packed), memkind))
+
+    def upload_frames_u8(self, f0, f1, frames, width_org, height_org, memkind=MEM_HOST):
+        """[frame][2][height_org][width_org][noc] 8-bit pairs; whole pyramid built on the device."""
+        self._ck(lib().ofdis_upload_frames_u8(self._h, f0, f1, _ptr(frames), width_org, height_org, memkind))
+
+    def get_flow_fullres(self, f0, f1, dst, width_org, height_org, memkind=MEM_HOST):
+        """Flow x 2^sc_l, upsampled to the original frame size and cropped (run_dense.cpp:407-414)."""
+        self._ck(lib().ofdis_get_flow_fullres(self._h, f0, f1, _ptr(dst), width_org, height_org, memkind))
 
     def upload_packed(self, f0, f1, packed, memkind=MEM_HOST):
         self._ck(lib().ofdis_upload_packed(self._h, f0, f1, _ptr(packed), memkind))

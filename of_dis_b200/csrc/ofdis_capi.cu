@@ -35,6 +35,12 @@ struct ofdis_ctx {
   size_t frame_floats = 0;
   size_t images_floats = 0;        // leading part of a packed frame that holds I0,I1 of all levels
   float* d_img = nullptr;          // [max_frames][frame_floats]
+  // lazily allocated staging of the pyramid / output stages (ofdis_upload_frames_u8,
+  // ofdis_upload_finest_level, ofdis_get_flow_fullres)
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  float* d_full = nullptr;
+  size_t full_floats = 0;
   std::vector<float*> d_flow;      // index level - sc_l, plus one extra entry for level sc_f+1 (initflow)
   std::vector<size_t> flow_floats;
   VarRefPlanes planes{};
@@ -263,6 +269,8 @@ int ofdis_destroy(ofdis_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
   cudaFree(ctx->d_img);
+  cudaFree(ctx->d_stage);
+  cudaFree(ctx->d_full);
   for (float* p : ctx->d_flow) cudaFree(p);
   for (LevelGeom& L : ctx->lev) {
     cudaFree(L.pat_p);
@@ -318,6 +326,17 @@ int ofdis_upload_level(ofdis_ctx* ctx, int frame, int level, const float* i0, co
   return OFDIS_OK;
 }
 
+int ofdis_get_level(ofdis_ctx* ctx, int frame, int level, int which, float* dst, int memkind) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  LevelGeom* L = level_of(ctx, level);
+  if (!L || frame < 0 || frame >= ctx->max_frames || which < 0 || which > 3 || !dst) return fail(ctx, OFDIS_ERR_ARG, "get_level: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)L->tmp_w * L->tmp_h * L->noc;
+  CK(cudaMemcpyAsync(dst, L->img[which] + (size_t)frame * L->img_fs[which], sizeof(float) * n, kind_out(memkind), ctx->stream));
+  if (memkind != OFDIS_MEM_DEVICE) CK(cudaStreamSynchronize(ctx->stream));
+  return OFDIS_OK;
+}
+
 size_t ofdis_packed_frame_floats(const ofdis_ctx* ctx) { return ctx ? ctx->frame_floats : 0; }
 
 size_t ofdis_packed_offset(const ofdis_ctx* ctx, int level, int which) {
@@ -353,6 +372,121 @@ int ofdis_upload_packed_images(ofdis_ctx* ctx, int f0, int f1, const float* pack
     if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "sobel_kernel launch", cudaGetLastError());
     ctx->launches += n;
   }
+  return OFDIS_OK;
+}
+
+// Coarser levels by 2x2 box means, then the gradients of I0 on every level.
+static int finish_pyramid(ofdis_ctx* ctx, int f0, int f1) {
+  for (int sl = ctx->prm.sc_l; sl <= ctx->prm.sc_f; ++sl) {
+    LevelGeom& L = ctx->lev[sl - ctx->prm.sc_l];
+    if (sl > ctx->prm.sc_l) {
+      if (launch_pyr_down(ctx->lev[sl - 1 - ctx->prm.sc_l], L, f0, f1, ctx->stream) < 0)
+        return fail(ctx, OFDIS_ERR_CUDA, "pyr_down_kernel launch", cudaGetLastError());
+      ctx->launches += 1;
+    }
+    if (launch_sobel(L, f0, f1, ctx->stream) < 0) return fail(ctx, OFDIS_ERR_CUDA, "sobel_kernel launch", cudaGetLastError());
+    ctx->launches += 1;
+  }
+  return OFDIS_OK;
+}
+
+static int ensure_stage(ofdis_ctx* ctx, size_t bytes) {
+  if (ctx->stage_bytes >= bytes) return OFDIS_OK;
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->d_stage);
+  ctx->d_stage = nullptr;
+  ctx->stage_bytes = 0;
+  if (cudaMalloc(&ctx->d_stage, bytes) != cudaSuccess) return fail(ctx, OFDIS_ERR_NOMEM, "staging buffer");
+  ctx->stage_bytes = bytes;
+  return OFDIS_OK;
+}
+
+static int org_padding(ofdis_ctx* ctx, int width_org, int height_org, int* padl, int* padt) {
+  // run_dense.cpp:299-311: pad up to the next multiple of 2^lv_f, floor(pad/2) on the left/top
+  const int scf = 1 << ctx->prm.sc_f;
+  if (width_org <= 0 || height_org <= 0 || (width_org + scf - 1) / scf * scf != ctx->width ||
+      (height_org + scf - 1) / scf * scf != ctx->height)
+    return fail(ctx, OFDIS_ERR_ARG, "frame size does not pad to the context's width/height");
+  *padl = (ctx->width - width_org) / 2;
+  *padt = (ctx->height - height_org) / 2;
+  return OFDIS_OK;
+}
+
+int ofdis_upload_frames_u8(ofdis_ctx* ctx, int f0, int f1, const unsigned char* frames, int width_org, int height_org,
+                           int memkind) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  if (f0 < 0 || f1 > ctx->max_frames || f0 >= f1 || !frames) return fail(ctx, OFDIS_ERR_ARG, "upload_frames_u8: bad argument");
+  if (ctx->prm.sc_l > 8) return fail(ctx, OFDIS_ERR_UNSUPPORTED, "upload_frames_u8: box sums are exact in float32 up to level 8");
+  PyrSourceU8 src;
+  int rc = org_padding(ctx, width_org, height_org, &src.pad_left, &src.pad_top);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  src.w_org = width_org;
+  src.h_org = height_org;
+  src.image_bytes = (size_t)width_org * height_org * ctx->prm.noc;
+  src.frames = frames;
+  if (memkind != OFDIS_MEM_DEVICE) {
+    const size_t bytes = src.image_bytes * 2 * (size_t)(f1 - f0);
+    rc = ensure_stage(ctx, src.image_bytes * 2 * (size_t)ctx->max_frames);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_stage, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    src.frames = static_cast<const unsigned char*>(ctx->d_stage);
+  }
+  if (launch_pyr_from_u8(ctx->lev[0], f0, f1, src, ctx->stream) < 0)
+    return fail(ctx, OFDIS_ERR_CUDA, "pyr_from_u8_kernel launch", cudaGetLastError());
+  ctx->launches += 1;
+  return finish_pyramid(ctx, f0, f1);
+}
+
+size_t ofdis_finest_level_frame_floats(const ofdis_ctx* ctx) {
+  return ctx ? (size_t)2 * ctx->lev[0].w * ctx->lev[0].h * ctx->lev[0].noc : 0;
+}
+
+int ofdis_upload_finest_level(ofdis_ctx* ctx, int f0, int f1, const float* packed, int memkind) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  if (f0 < 0 || f1 > ctx->max_frames || f0 >= f1 || !packed) return fail(ctx, OFDIS_ERR_ARG, "upload_finest_level: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const size_t per = ofdis_finest_level_frame_floats(ctx);
+  const float* src = packed;
+  if (memkind != OFDIS_MEM_DEVICE) {
+    int rc = ensure_stage(ctx, sizeof(float) * per * (size_t)ctx->max_frames);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_stage, packed, sizeof(float) * per * (size_t)(f1 - f0), cudaMemcpyHostToDevice, ctx->stream));
+    src = static_cast<const float*>(ctx->d_stage);
+  }
+  if (launch_pyr_from_level(ctx->lev[0], f0, f1, src, ctx->stream) < 0)
+    return fail(ctx, OFDIS_ERR_CUDA, "pyr_from_level_kernel launch", cudaGetLastError());
+  ctx->launches += 1;
+  return finish_pyramid(ctx, f0, f1);
+}
+
+int ofdis_get_flow_fullres(ofdis_ctx* ctx, int f0, int f1, float* out, int width_org, int height_org, int memkind) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  if (f0 < 0 || f1 > ctx->max_frames || f0 >= f1 || !out) return fail(ctx, OFDIS_ERR_ARG, "get_flow_fullres: bad argument");
+  int cx, cy;
+  int rc = org_padding(ctx, width_org, height_org, &cx, &cy);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t per = (size_t)width_org * height_org * ctx->nop;
+  float* dst = out;
+  if (memkind != OFDIS_MEM_DEVICE) {
+    const size_t need = per * (size_t)ctx->max_frames;
+    if (ctx->full_floats < need) {
+      CK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_full);
+      ctx->d_full = nullptr;
+      ctx->full_floats = 0;
+      if (cudaMalloc((void**)&ctx->d_full, sizeof(float) * need) != cudaSuccess)
+        return fail(ctx, OFDIS_ERR_NOMEM, "full-resolution flow buffer");
+      ctx->full_floats = need;
+    }
+    dst = ctx->d_full;
+  }
+  if (launch_flow_upsample(ctx->lev[0], f0, f1, dst, width_org, height_org, cx, cy, ctx->stream) < 0)
+    return fail(ctx, OFDIS_ERR_CUDA, "flow_upsample_kernel launch", cudaGetLastError());
+  ctx->launches += 1;
+  if (memkind != OFDIS_MEM_DEVICE)
+    CK(cudaMemcpyAsync(out, dst, sizeof(float) * per * (size_t)(f1 - f0), cudaMemcpyDeviceToHost, ctx->stream));
   return OFDIS_OK;
 }
 

@@ -91,7 +91,18 @@ struct ProfScope {
 int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int f1, bool init_from_coarser,
                           cudaStream_t st, Profiler* prof = nullptr);
 int launch_densify(const LevelGeom& g, int f0, int f1, cudaStream_t st, Profiler* prof = nullptr);
+// pyramid_kernels.cu -- callers either side of the hot path
+struct PyrSourceU8 {
+  const unsigned char* frames;  // [frame][2][h_org][w_org][noc], device
+  size_t image_bytes;           // h_org * w_org * noc
+  int w_org, h_org, pad_left, pad_top;
+};
 int launch_sobel(const LevelGeom& g, int f0, int f1, cudaStream_t st);
+int launch_pyr_from_u8(const LevelGeom& g, int f0, int f1, const PyrSourceU8& s, cudaStream_t st);
+int launch_pyr_from_level(const LevelGeom& g, int f0, int f1, const float* stage, cudaStream_t st);
+int launch_pyr_down(const LevelGeom& gs, const LevelGeom& gd, int f0, int f1, cudaStream_t st);
+int launch_flow_upsample(const LevelGeom& g, int f0, int f1, float* out, int w_org, int h_org, int crop_x, int crop_y,
+                         cudaStream_t st);
 int launch_varref(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
                   cudaStream_t st, Profiler* prof = nullptr);
 

@@ -566,49 +566,7 @@ __global__ void __launch_bounds__(256) densify_kernel(LevelGeom g, int f0) {
 }
 
 
-// Gradients of I0 on the device (the first "next" row of SURVEY 8f): cv::Sobel(CV_32F, 3x3,
-// scale 1/8, BORDER_DEFAULT = reflect101) on the un-padded level image, zero border of width
-// `pad` (run_dense.cpp:156-157,171-172).  Same expression order as of_dis_b200/preprocess.py
-// (row difference first, then the [1 2 1]/8 column sum, and vice versa for dy); for images that
-// come from 8-bit input every intermediate is exact, so this equals OpenCV bit for bit.
-__global__ void __launch_bounds__(256) sobel_kernel(LevelGeom g, int f0) {
-  const int xp = blockIdx.x * blockDim.x + threadIdx.x, yp = blockIdx.y * blockDim.y + threadIdx.y;
-  const int frame = f0 + blockIdx.z;
-  if (xp >= g.tmp_w || yp >= g.tmp_h) return;
-  const int C = g.noc, w = g.w, h = g.h, P = g.pad;
-  const float* im = g.img[0] + (size_t)frame * g.img_fs[0];
-  float* gx = const_cast<float*>(g.img[1]) + (size_t)frame * g.img_fs[1];
-  float* gy = const_cast<float*>(g.img[2]) + (size_t)frame * g.img_fs[2];
-  const int x = xp - P, y = yp - P;
-  const size_t o = ((size_t)yp * g.tmp_w + xp) * C;
-  if (x < 0 || y < 0 || x >= w || y >= h) {
-    for (int c = 0; c < C; ++c) {
-      gx[o + c] = 0.f;
-      gy[o + c] = 0.f;
-    }
-    return;
-  }
-  auto r101 = [](int v, int n) { return n == 1 ? 0 : (v < 0 ? -v : (v >= n ? 2 * (n - 1) - v : v)); };
-  const int xm = r101(x - 1, w) + P, x0 = x + P, xq = r101(x + 1, w) + P;
-  const int ym = r101(y - 1, h) + P, y0 = y + P, yq = r101(y + 1, h) + P;
-  for (int c = 0; c < C; ++c) {
-#define IM(X, Y) im[((size_t)(Y) * g.tmp_w + (X)) * C + c]
-    const float t0 = IM(xq, ym) - IM(xm, ym), t1 = IM(xq, y0) - IM(xm, y0), t2 = IM(xq, yq) - IM(xm, yq);
-    gx[o + c] = (t0 * 0.125f + t1 * 0.25f) + t2 * 0.125f;
-    const float s0 = (IM(xm, ym) * 0.125f + IM(x0, ym) * 0.25f) + IM(xq, ym) * 0.125f;
-    const float s2 = (IM(xm, yq) * 0.125f + IM(x0, yq) * 0.25f) + IM(xq, yq) * 0.125f;
-    gy[o + c] = s2 - s0;
-#undef IM
-  }
-}
-
 }  // namespace
-
-int launch_sobel(const LevelGeom& g, int f0, int f1, cudaStream_t st) {
-  const dim3 block(32, 8), grid((g.tmp_w + 31) / 32, (g.tmp_h + 7) / 8, f1 - f0);
-  sobel_kernel<<<grid, block, 0, st>>>(g, f0);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
 
 int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int f1, bool init_from_coarser,
                           cudaStream_t st, Profiler* prof) {

@@ -239,3 +239,79 @@ def test_images_only_upload_derives_the_same_gradients_on_device(ch, api):
     for f in range(nfr):
         assert_bits(ctx.get_flow(f, prm.sc_l), ref[f], "frame %d" % f)
     ctx.close()
+
+
+def _frames_u8(pairs):
+    """[frame][2][h][w][C] uint8 block as ofdis_upload_frames_u8 takes it."""
+    return np.ascontiguousarray(np.stack([np.stack([a, b]) for a, b in pairs]))
+
+
+@pytest.mark.parametrize("ch,size", [(1, (436, 1024)), (3, (121, 203)), (1, (128, 256))])
+def test_device_pyramid_from_8bit_frames_equals_the_host_pyramid(ch, size, api):
+    """ofdis_upload_frames_u8 (divisibility padding, box-mean levels, Sobel/8, border padding on the
+    device; run_dense.cpp:130-178,298-311) reproduces preprocess.PairPyramids bit for bit -- every
+    padded array of every level -- and therefore the same flow."""
+    prm = params.operating_point(2, size[1], noc=ch) if size[1] >= 256 else \
+        params.from_cli_numbers("3 1 8 8 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split(), noc=ch)
+    nfr = 2
+    pairs = [synth.synthetic_pair(size[0], size[1], ch, seed=70 + s)[:2] for s in range(nfr)]
+    pyrs = [preprocess.PairPyramids(a, b, prm.sc_f, prm.p_samp_s) for a, b in pairs]
+    ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, nfr)
+    ctx.upload_frames_u8(0, nfr, _frames_u8(pairs), size[1], size[0])
+    for f, p in enumerate(pyrs):
+        for lv in range(prm.sc_l, prm.sc_f + 1):
+            for which, exp in enumerate((p.i0[lv], p.i0x[lv], p.i0y[lv], p.i1[lv])):
+                assert_bits(ctx.get_level(f, lv, which), exp, "frame %d level %d array %d" % (f, lv, which))
+    ctx.run(nfr)
+    got = [ctx.get_flow(f, prm.sc_l) for f in range(nfr)]
+    for f, p in enumerate(pyrs):
+        ctx.upload_pyramids(f, p)
+    ctx.run(nfr)
+    for f in range(nfr):
+        assert_bits(got[f], ctx.get_flow(f, prm.sc_l), "flow of frame %d" % f)
+    ctx.close()
+
+
+@pytest.mark.parametrize("ch", [1, 3])
+def test_finest_level_upload_derives_the_rest_on_device(ch, api):
+    """ofdis_upload_finest_level: un-padded I0,I1 of level sc_l in, everything else derived."""
+    prm = params.from_cli_numbers("4 2 8 8 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split(), noc=ch)
+    nfr = 3
+    pairs = [synth.synthetic_pair(144, 208, ch, seed=80 + s)[:2] for s in range(nfr)]
+    pyrs = [preprocess.PairPyramids(a, b, prm.sc_f, prm.p_samp_s) for a, b in pairs]
+    ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, nfr)
+    P, l = pyrs[0].imgpadding, prm.sc_l
+    packed = np.ascontiguousarray(np.stack([np.stack([p.i0[l][P:-P, P:-P], p.i1[l][P:-P, P:-P]]) for p in pyrs]))
+    assert packed[0].size == ctx.finest_level_frame_floats
+    ctx.upload_finest_level(0, nfr, packed)
+    for f, p in enumerate(pyrs):
+        for lv in range(prm.sc_l, prm.sc_f + 1):
+            for which, exp in enumerate((p.i0[lv], p.i0x[lv], p.i0y[lv], p.i1[lv])):
+                assert_bits(ctx.get_level(f, lv, which), exp, "frame %d level %d array %d" % (f, lv, which))
+    ctx.close()
+
+
+@pytest.mark.parametrize("nop,size,op", [(2, (436, 1024), 2), (1, (121, 203), None), (2, (64, 128), 0)])
+def test_fullres_output_stage_equals_postprocess(nop, size, op, api):
+    """ofdis_get_flow_fullres (x2^lv_l, bilinear x2^lv_l, crop; run_dense.cpp:407-414) ==
+    preprocess.postprocess of the level flow, bit for bit."""
+    if op == 2:
+        prm = params.operating_point(2, size[1], nop=nop)
+    elif op == 0:  # lv_l = 0: plain crop
+        prm = params.from_cli_numbers("2 0 8 8 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split(), nop=nop)
+    else:
+        prm = params.from_cli_numbers("3 1 8 8 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split(), nop=nop)
+    nfr = 2
+    pairs = [synth.synthetic_pair(size[0], size[1], 1, seed=90 + s)[:2] for s in range(nfr)]
+    pyrs = [preprocess.PairPyramids(a, b, prm.sc_f, prm.p_samp_s) for a, b in pairs]
+    ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, nfr)
+    for f, p in enumerate(pyrs):
+        ctx.upload_pyramids(f, p)
+    ctx.run(nfr)
+    out = np.empty((nfr, size[0], size[1], nop), np.float32)
+    ctx.get_flow_fullres(0, nfr, out, size[1], size[0])
+    ctx.sync()
+    for f, p in enumerate(pyrs):
+        exp = preprocess.postprocess(ctx.get_flow(f, prm.sc_l), prm.sc_l, p.padw, p.padh, size[1], size[0])
+        assert_bits(out[f], exp.reshape(out[f].shape), "frame %d" % f)
+    ctx.close()
