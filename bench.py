@@ -192,8 +192,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--lanes", type=int, default=8, help="contexts/streams whose steps overlap")
-    ap.add_argument("--e2e-upload", choices=("images", "pyramids"), default="images",
-                    help="e2e H2D payload: I0,I1 of every level (gradients derived on the device) or all four arrays")
+    ap.add_argument("--e2e-upload", choices=("finest", "images", "pyramids"), default="finest",
+                    help="e2e H2D payload: I0,I1 of the finest used level (coarser levels, gradients and paddings derived "
+                         "on the device), I0,I1 of every level, or all four arrays of every level as OFClass takes them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -304,16 +305,31 @@ def main():
     # Every step copies its own inputs from pinned host memory and its flows back.  No L2 flush is
     # possible inside an overlapped region; the two alternating working sets (2 x ~2 MB per pair)
     # exceed L2 at the default batch.
-    # e2e transfers only I0,I1 of every level (the gradients of I0 are derived on the device by
-    # ofdis_upload_packed_images -- inside the timed region); that halves the PCIe bytes per pair
+    # Default e2e payload: the un-padded I0,I1 of the finest level the run uses; coarser levels (2x2
+    # box means), Sobel gradients and border paddings are derived on the device inside the timed
+    # region (ofdis_upload_finest_level).  --e2e-upload pyramids ships all four padded arrays of
+    # every level exactly as OFClass's constructor takes them.
     n_img = ctx.packed_images_frame_floats
+    n_fin = ctx.finest_level_frame_floats
     host_img = torch.empty((B, n_img), dtype=torch.float32).pin_memory()
     host_img.copy_(host_in[:, :n_img])
-
-    images_only = args.e2e_upload == "images"
+    host_fin = torch.empty((B, n_fin), dtype=torch.float32).pin_memory()
+    P_ = pyrs[0].imgpadding
+    for f, p in enumerate(pyrs):
+        fin = np.stack([p.i0[prm.sc_l][P_:-P_, P_:-P_], p.i1[prm.sc_l][P_:-P_, P_:-P_]])
+        host_fin[f].numpy()[:] = fin.reshape(-1)
+    mode = args.e2e_upload
+    h2d_floats = {"finest": n_fin, "images": n_img, "pyramids": ff}[mode]
+    h2d_payload = {"finest": "un-padded I0,I1 of level %d; levels %d..%d, I0x,I0y and paddings derived on the device "
+                             "inside the timed region" % (prm.sc_l, prm.sc_l + 1, prm.sc_f),
+                   "images": "padded I0,I1 of levels %d..%d; I0x,I0y derived on the device inside the timed region"
+                             % (prm.sc_l, prm.sc_f),
+                   "pyramids": "padded I0,I0x,I0y,I1 of levels %d..%d" % (prm.sc_l, prm.sc_f)}[mode]
 
     def upload(c, b=B):
-        if images_only:
+        if mode == "finest":
+            c.upload_finest_level(0, b, host_fin.data_ptr())
+        elif mode == "images":
             c.upload_packed_images(0, b, host_img.data_ptr())
         else:
             c.upload_packed(0, b, host_in.data_ptr())
@@ -332,6 +348,16 @@ def main():
         n_warm_e2e += 1
         if n_warm_e2e % NL == 0:
             torch.cuda.synchronize()
+    barrier()
+    # the e2e path must produce the flows of the resident path (same pairs), bit for bit
+    resident_flow = torch.empty((B, flow_floats), dtype=torch.float32)
+    ctx.upload_packed(0, B, host_in.data_ptr())
+    ctx.run(B)
+    ctx.get_flow_batch(0, B, resident_flow.data_ptr())
+    ctx.sync()
+    e2e_step(0)
+    torch.cuda.synchronize()
+    e2e_same = bool(torch.equal(resident_flow.view(torch.int32), host_out.view(torch.int32)))
     barrier()
     w0 = time.perf_counter()
     ms_e2e = maxrank(pipelined(e2e_step, args.steps))
@@ -423,10 +449,8 @@ def main():
         "single_lane": {"ms_per_step": ms_res_single, "value": pix / (ms_res_single * 1e-3) / 1e6,
                         "note": "one context, one stream, L2 flushed before every step"},
         "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
-                "h2d_bytes_per_step": int(B * (n_img if images_only else ff) * 4),
-                "h2d_payload": "I0,I1 of levels %d..%d (I0x,I0y derived on the device inside the timed region)"
-                               % (prm.sc_f, prm.sc_l) if images_only else "I0,I0x,I0y,I1 of every level",
-                "host_numa_node": numa_node, "warmup_steps": n_warm_e2e, "d2h_bytes_per_step": int(B * flow_floats * 4),
+                "h2d_bytes_per_step": int(B * h2d_floats * 4), "h2d_payload": h2d_payload,
+                "host_numa_node": numa_node, "warmup_steps": n_warm_e2e, "flows_equal_resident_path": e2e_same, "d2h_bytes_per_step": int(B * flow_floats * 4),
                 "mode": "%d lanes (context+stream), step i on lane i %% lanes: copies and kernels of consecutive steps overlap" % NL,
                 "serial_ms_per_step": ms_e2e_serial,
                 "serial_value": pix / (ms_e2e_serial * 1e-3) / 1e6},
