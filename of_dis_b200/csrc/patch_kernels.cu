@@ -229,9 +229,10 @@ __global__ void __launch_bounds__(256) patch_optimize_kernel(LevelGeom g, PatchP
         if (cnt == 1) dpsq_init = dpsq;
         mares_old = mares;
         mares = sw / fn;
-        const bool go = (cnt < pp.max_iter) & (mares > pp.res_thresh) &
-                        ((cnt < pp.min_iter) | (dpsq / dpsq_init >= pp.dp_thresh_sq)) &
-                        ((cnt < pp.min_iter) | (mares / mares_old <= pp.dr_thresh));
+        // the two ratio tests only count once min_iter is reached: skip their divisions before
+        bool go = (cnt < pp.max_iter) & (mares > pp.res_thresh);
+        if (go && cnt >= pp.min_iter)
+          go = (dpsq / dpsq_init >= pp.dp_thresh_sq) & (mares / mares_old <= pp.dr_thresh);
         if (!go) {
           conv = 1;
           active = false;
@@ -396,11 +397,11 @@ __global__ void __launch_bounds__(256) patch_p8c1_kernel(LevelGeom g, PatchParam
         const float rx = ptx - (float)pfx, ry = pty - (float)pfy;
         const float w0 = rx * ry, w1 = (1.f - rx) * ry, w2 = rx * (1.f - ry), w3 = (1.f - rx) * (1.f - ry);
         // window rows pcy-5 .. pcy+3, columns (pcx-5+l8) and (pcx-4+l8): d/c above, b/a below
-        const float* q = i1 + (pcx + g.pad - P / 2 - 1 + l8) + (pcy + g.pad - P / 2 - 1) * tw;
-        float cl = __ldg(q), cr = __ldg(q + 1);  // row above: d, c
+        const float* q0 = i1 + (pcx + g.pad - P / 2 - 1 + l8) + (pcy + g.pad - P / 2 - 1) * tw;
+        float cl = __ldg(q0), cr = __ldg(q0 + 1);  // row above: d, c
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          q += tw;
+          const float* q = q0 + (k + 1) * tw;  // one IMAD.WIDE per row instead of a 64-bit add chain
           const float bl = __ldg(q), br = __ldg(q + 1);  // this row: b, a
           V[k] = w0 * br + w1 * bl + w2 * cr + w3 * cl;
           acc = (k == 0) ? V[k] : acc + V[k];
@@ -455,9 +456,10 @@ __global__ void __launch_bounds__(256) patch_p8c1_kernel(LevelGeom g, PatchParam
         if (cnt == 1) dpsq_init = dpsq;
         mares_old = mares;
         mares = sw / fn;
-        const bool go = (cnt < pp.max_iter) & (mares > pp.res_thresh) &
-                        ((cnt < pp.min_iter) | (dpsq / dpsq_init >= pp.dp_thresh_sq)) &
-                        ((cnt < pp.min_iter) | (mares / mares_old <= pp.dr_thresh));
+        // the two ratio tests only count once min_iter is reached: skip their divisions before
+        bool go = (cnt < pp.max_iter) & (mares > pp.res_thresh);
+        if (go && cnt >= pp.min_iter)
+          go = (dpsq / dpsq_init >= pp.dp_thresh_sq) & (mares / mares_old <= pp.dr_thresh);
         if (!go) {
           conv = 1;
           active = false;

@@ -643,13 +643,15 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   const int tma_threads = K * hpad + 32;
   const size_t tma_smem = (size_t)sor_tma_stages(K) * ((NOP == 2 ? 8 : 5) + 2) * hpad * 16 +
                           sizeof(float4) * 2 * (size_t)K * (g.h + 2) * nf4 + 8 * (size_t)sor_tma_stages(K);
+  static const long exp_min_smem = getenv("OFDIS_EXP_SOR_SMEM_KB") ? atol(getenv("OFDIS_EXP_SOR_SMEM_KB")) * 1024 : 0;
+  const size_t tma_smem_req = tma_smem < (size_t)exp_min_smem ? (size_t)exp_min_smem : tma_smem;
   const bool use_tma = (K >= 1) && tma_threads <= 288 && tma_smem <= 200 * 1024 &&
                        (hpad == 32 || hpad == 64 || hpad == 128 || hpad == 256);
   auto launch_tma = [&]() {
 #define SOR_TMA_LAUNCH(HP)                                                                             \
   do {                                                                                                 \
-    cudaFuncSetAttribute(sor_tma_kernel<NOP, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem); \
-    sor_tma_kernel<NOP, HP><<<nf, tma_threads, tma_smem, st>>>(g, pl, vp, K);                            \
+    cudaFuncSetAttribute(sor_tma_kernel<NOP, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_req); \
+    sor_tma_kernel<NOP, HP><<<nf, tma_threads, tma_smem_req, st>>>(g, pl, vp, K);                            \
   } while (0)
     if (hpad == 32) SOR_TMA_LAUNCH(32);
     else if (hpad == 64) SOR_TMA_LAUNCH(64);
