@@ -115,6 +115,113 @@ void FillCamParam(camparam& cp, const optparam& op, int width_full, int height_f
 }
 
 // ---------------------------------------------------------------------------
+namespace {
+
+// What the level loop starts from and where its result goes: the reference's float pyramids and
+// level-sc_l flow (oflow.h:84-111), or -- extension -- 8-bit frames in and full-resolution flow out
+// with pyramid, gradients, paddings, upsampling and crop on the device (run_dense.cpp:130-178,
+// 298-311,407-414).
+struct RunIO {
+  const float **im_ao = nullptr, **im_ao_dx = nullptr, **im_ao_dy = nullptr, **im_bo = nullptr;
+  const unsigned char* frames = nullptr;  // [2][height_org][width_org][noc]
+  int width_org = 0, height_org = 0;
+  float* outflow = nullptr;
+  const float* initflow = nullptr;
+};
+
+void run_ofclass(const RunIO& io, const ofdis_params& p, int nop, int width, int height, int imgpadding, int device) {
+  timeval t0, t1;
+  const int verbosity = p.verbosity, sc_f = p.sc_f, sc_l = p.sc_l;
+  if (verbosity > 0) gettimeofday(&t0, nullptr);
+  ofdis_ctx* ctx = nullptr;
+  check(ofdis_create(&ctx, device, nullptr, &p, nop, width, height, imgpadding, 1), nullptr, "ofdis_create");
+  try {
+    if (verbosity > 1) {
+      gettimeofday(&t1, nullptr);
+      printf("TIME (Grid Memo. Alloc. ) (ms): %3g\n", ms_between(t0, t1));
+    }
+    if (io.frames)
+      check(ofdis_upload_frames_u8(ctx, 0, 1, io.frames, io.width_org, io.height_org, OFDIS_MEM_HOST), ctx,
+            "ofdis_upload_frames_u8");
+    else
+      for (int sl = sc_l; sl <= sc_f; ++sl)
+        check(ofdis_upload_level(ctx, 0, sl, io.im_ao[sl], io.im_ao_dx[sl], io.im_ao_dy[sl], io.im_bo[sl],
+                                 OFDIS_MEM_HOST),
+              ctx, "ofdis_upload_level");
+    if (io.initflow) check(ofdis_set_flow(ctx, 0, sc_f + 1, io.initflow, OFDIS_MEM_HOST), ctx, "ofdis_set_flow");
+    if (verbosity > 1) {
+      // per-level timing like oflow.cpp:303 (stages are timed with a stream sync each)
+      for (int sl = sc_f; sl >= sc_l; --sl) {
+        timeval a, b, c, d;
+        int w, h, nopw, noph, steps;
+        ofdis_level_info(ctx, sl, &w, &h, &nopw, &noph, &steps);
+        ofdis_sync(ctx);
+        gettimeofday(&a, nullptr);
+        check(ofdis_patgrid_optimize(ctx, sl, 0, 1, (sl < sc_f) || io.initflow), ctx, "patgrid_optimize");
+        ofdis_sync(ctx);
+        gettimeofday(&b, nullptr);
+        check(ofdis_patgrid_aggregate(ctx, sl, 0, 1), ctx, "patgrid_aggregate");
+        ofdis_sync(ctx);
+        gettimeofday(&c, nullptr);
+        if (p.usetvref) check(ofdis_varref_refine(ctx, sl, 0, 1), ctx, "varref_refine");
+        ofdis_sync(ctx);
+        gettimeofday(&d, nullptr);
+        printf("TIME (Sc: %i, #p:%6i, pconst, pinit, poptim, cflow, tvopt, total): %8.2f %8.2f %8.2f %8.2f %8.2f -> %8.2f ms.\n",
+               sl, nopw * noph, 0.0, 0.0, ms_between(a, b), ms_between(b, c), ms_between(c, d), ms_between(a, d));
+      }
+    } else {
+      check(ofdis_run(ctx, 1, io.initflow ? 1 : 0), ctx, "ofdis_run");
+    }
+    if (io.frames) {
+      check(ofdis_get_flow_fullres(ctx, 0, 1, io.outflow, io.width_org, io.height_org, OFDIS_MEM_HOST), ctx,
+            "ofdis_get_flow_fullres");
+      check(ofdis_sync(ctx), ctx, "ofdis_sync");
+    } else {
+      check(ofdis_get_flow(ctx, 0, sc_l, io.outflow, OFDIS_MEM_HOST), ctx, "ofdis_get_flow");
+    }
+  } catch (...) {
+    ofdis_destroy(ctx);
+    throw;
+  }
+  ofdis_destroy(ctx);
+  if (verbosity > 0) {
+    gettimeofday(&t1, nullptr);
+    printf("TIME (O.Flow Run-Time   ) (ms): %3g\n", ms_between(t0, t1));
+  }
+}
+
+ofdis_params make_params(int sc_f, int sc_l, int max_iter, int min_iter, float dp_thresh, float dr_thresh,
+                         float res_thresh, int p_samp_s, float patove, bool usefbcon, int costfct, int noc, int patnorm,
+                         bool usetvref, float tv_alpha, float tv_gamma, float tv_delta, int tv_innerit, int tv_solverit,
+                         float tv_sor, int verbosity) {
+  ofdis_params p;
+  std::memset(&p, 0, sizeof(p));
+  p.sc_f = sc_f;
+  p.sc_l = sc_l;
+  p.max_iter = max_iter;
+  p.min_iter = min_iter;
+  p.dp_thresh = dp_thresh;
+  p.dr_thresh = dr_thresh;
+  p.res_thresh = res_thresh;
+  p.p_samp_s = p_samp_s;
+  p.patove = patove;
+  p.usefbcon = usefbcon ? 1 : 0;
+  p.costfct = costfct;
+  p.noc = noc;
+  p.patnorm = patnorm;
+  p.usetvref = usetvref ? 1 : 0;
+  p.tv_alpha = tv_alpha;
+  p.tv_gamma = tv_gamma;
+  p.tv_delta = tv_delta;
+  p.tv_innerit = tv_innerit;
+  p.tv_solverit = tv_solverit;
+  p.tv_sor = tv_sor;
+  p.verbosity = verbosity;
+  return p;
+}
+
+}  // namespace
+
 OFClass::OFClass(const float** im_ao_in, const float** im_ao_dx_in, const float** im_ao_dy_in,
                  const float** im_bo_in, const float** im_bo_dx_in, const float** im_bo_dy_in,
                  const int imgpadding_in, float* outflow, const float* initflow, const int width_in,
@@ -127,77 +234,44 @@ OFClass::OFClass(const float** im_ao_in, const float** im_ao_dx_in, const float*
                  const int verbosity_in, const int nop_in, const int device) {
   (void)im_bo_dx_in;
   (void)im_bo_dy_in;  // never read by the reference either (patch.cpp:90-97)
-  timeval t0, t1;
-  if (verbosity_in > 0) gettimeofday(&t0, nullptr);
-  ofdis_params p;
-  std::memset(&p, 0, sizeof(p));
-  p.sc_f = sc_f_in;
-  p.sc_l = sc_l_in;
-  p.max_iter = max_iter_in;
-  p.min_iter = min_iter_in;
-  p.dp_thresh = dp_thresh_in;
-  p.dr_thresh = dr_thresh_in;
-  p.res_thresh = res_thresh_in;
-  p.p_samp_s = padval_in;
-  p.patove = patove_in;
-  p.usefbcon = usefbcon_in ? 1 : 0;
-  p.costfct = costfct_in;
-  p.noc = noc_in;
-  p.patnorm = patnorm_in;
-  p.usetvref = usetvref_in ? 1 : 0;
-  p.tv_alpha = tv_alpha_in;
-  p.tv_gamma = tv_gamma_in;
-  p.tv_delta = tv_delta_in;
-  p.tv_innerit = tv_innerit_in;
-  p.tv_solverit = tv_solverit_in;
-  p.tv_sor = tv_sor_in;
-  p.verbosity = verbosity_in;
-  ofdis_ctx* ctx = nullptr;
-  check(ofdis_create(&ctx, device, nullptr, &p, nop_in, width_in, height_in, imgpadding_in, 1), nullptr,
-        "ofdis_create");
-  try {
-    if (verbosity_in > 1) {
-      gettimeofday(&t1, nullptr);
-      printf("TIME (Grid Memo. Alloc. ) (ms): %3g\n", ms_between(t0, t1));
-    }
-    for (int sl = sc_l_in; sl <= sc_f_in; ++sl)
-      check(ofdis_upload_level(ctx, 0, sl, im_ao_in[sl], im_ao_dx_in[sl], im_ao_dy_in[sl], im_bo_in[sl],
-                               OFDIS_MEM_HOST),
-            ctx, "ofdis_upload_level");
-    if (initflow) check(ofdis_set_flow(ctx, 0, sc_f_in + 1, initflow, OFDIS_MEM_HOST), ctx, "ofdis_set_flow");
-    if (verbosity_in > 1) {
-      // per-level timing like oflow.cpp:303 (stages are timed with a stream sync each)
-      for (int sl = sc_f_in; sl >= sc_l_in; --sl) {
-        timeval a, b, c, d;
-        int w, h, nopw, noph, steps;
-        ofdis_level_info(ctx, sl, &w, &h, &nopw, &noph, &steps);
-        ofdis_sync(ctx);
-        gettimeofday(&a, nullptr);
-        check(ofdis_patgrid_optimize(ctx, sl, 0, 1, (sl < sc_f_in) || initflow), ctx, "patgrid_optimize");
-        ofdis_sync(ctx);
-        gettimeofday(&b, nullptr);
-        check(ofdis_patgrid_aggregate(ctx, sl, 0, 1), ctx, "patgrid_aggregate");
-        ofdis_sync(ctx);
-        gettimeofday(&c, nullptr);
-        if (usetvref_in) check(ofdis_varref_refine(ctx, sl, 0, 1), ctx, "varref_refine");
-        ofdis_sync(ctx);
-        gettimeofday(&d, nullptr);
-        printf("TIME (Sc: %i, #p:%6i, pconst, pinit, poptim, cflow, tvopt, total): %8.2f %8.2f %8.2f %8.2f %8.2f -> %8.2f ms.\n",
-               sl, nopw * noph, 0.0, 0.0, ms_between(a, b), ms_between(b, c), ms_between(c, d), ms_between(a, d));
-      }
-    } else {
-      check(ofdis_run(ctx, 1, initflow ? 1 : 0), ctx, "ofdis_run");
-    }
-    check(ofdis_get_flow(ctx, 0, sc_l_in, outflow, OFDIS_MEM_HOST), ctx, "ofdis_get_flow");
-  } catch (...) {
-    ofdis_destroy(ctx);
-    throw;
-  }
-  ofdis_destroy(ctx);
-  if (verbosity_in > 0) {
-    gettimeofday(&t1, nullptr);
-    printf("TIME (O.Flow Run-Time   ) (ms): %3g\n", ms_between(t0, t1));
-  }
+  RunIO io;
+  io.im_ao = im_ao_in;
+  io.im_ao_dx = im_ao_dx_in;
+  io.im_ao_dy = im_ao_dy_in;
+  io.im_bo = im_bo_in;
+  io.outflow = outflow;
+  io.initflow = initflow;
+  run_ofclass(io,
+              make_params(sc_f_in, sc_l_in, max_iter_in, min_iter_in, dp_thresh_in, dr_thresh_in, res_thresh_in,
+                          padval_in, patove_in, usefbcon_in, costfct_in, noc_in, patnorm_in, usetvref_in, tv_alpha_in,
+                          tv_gamma_in, tv_delta_in, tv_innerit_in, tv_solverit_in, tv_sor_in, verbosity_in),
+              nop_in, width_in, height_in, imgpadding_in, device);
+}
+
+OFClass::OFClass(const unsigned char* frame_ao, const unsigned char* frame_bo, const int width_org,
+                 const int height_org, float* outflow_fullres, const float* initflow, const int sc_f_in,
+                 const int sc_l_in, const int max_iter_in, const int min_iter_in, const float dp_thresh_in,
+                 const float dr_thresh_in, const float res_thresh_in, const int padval_in, const float patove_in,
+                 const bool usefbcon_in, const int costfct_in, const int noc_in, const int patnorm_in,
+                 const bool usetvref_in, const float tv_alpha_in, const float tv_gamma_in, const float tv_delta_in,
+                 const int tv_innerit_in, const int tv_solverit_in, const float tv_sor_in, const int verbosity_in,
+                 const int nop_in, const int device) {
+  const size_t n = (size_t)width_org * height_org * noc_in;
+  std::vector<unsigned char> frames(2 * n);
+  std::memcpy(frames.data(), frame_ao, n);
+  std::memcpy(frames.data() + n, frame_bo, n);
+  const int scf = 1 << sc_f_in;  // run_dense.cpp:298-311
+  RunIO io;
+  io.frames = frames.data();
+  io.width_org = width_org;
+  io.height_org = height_org;
+  io.outflow = outflow_fullres;
+  io.initflow = initflow;
+  run_ofclass(io,
+              make_params(sc_f_in, sc_l_in, max_iter_in, min_iter_in, dp_thresh_in, dr_thresh_in, res_thresh_in,
+                          padval_in, patove_in, usefbcon_in, costfct_in, noc_in, patnorm_in, usetvref_in, tv_alpha_in,
+                          tv_gamma_in, tv_delta_in, tv_innerit_in, tv_solverit_in, tv_sor_in, verbosity_in),
+              nop_in, (width_org + scf - 1) / scf * scf, (height_org + scf - 1) / scf * scf, padval_in, device);
 }
 
 // ---------------------------------------------------------------------------

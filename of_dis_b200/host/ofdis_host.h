@@ -76,6 +76,16 @@ class OFClass {
           const bool usetvref_in, const float tv_alpha_in, const float tv_gamma_in, const float tv_delta_in,
           const int tv_innerit_in, const int tv_solverit_in, const float tv_sor_in, const int verbosity_in,
           const int nop_in = 2, const int device = 0);
+  // Extension: 8-bit frames ([height_org][width_org][noc]) in, flow of the
+  // original frame size out; divisibility padding, pyramid, gradients, border padding, x2^sc_l
+  // upsampling and crop (run_dense.cpp:130-178,298-311,407-414) run on the device.
+  OFClass(const unsigned char* frame_ao, const unsigned char* frame_bo, const int width_org, const int height_org,
+          float* outflow_fullres, const float* initflow, const int sc_f_in, const int sc_l_in, const int max_iter_in,
+          const int min_iter_in, const float dp_thresh_in, const float dr_thresh_in, const float res_thresh_in,
+          const int padval_in, const float patove_in, const bool usefbcon_in, const int costfct_in, const int noc_in,
+          const int patnorm_in, const bool usetvref_in, const float tv_alpha_in, const float tv_gamma_in,
+          const float tv_delta_in, const int tv_innerit_in, const int tv_solverit_in, const float tv_sor_in,
+          const int verbosity_in, const int nop_in = 2, const int device = 0);
 };
 
 class PatGridClass {

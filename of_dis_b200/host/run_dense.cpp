@@ -423,6 +423,32 @@ int main(int argc, char** argv) {
     return pad(f, (int)floor((float)padh / 2.0f), (int)ceil((float)padh / 2.0f), (int)floor((float)padw / 2.0f),
                (int)ceil((float)padw / 2.0f), true);
   };
+  // Default: pyramid, gradients, paddings, upsampling and crop run on the device, bit-identical to
+  // the host restatement below (tests/test_gpu_parity.py); OFDIS_HOST_PYRAMID=1 keeps them on the
+  // host and hands OFClass the float pyramids exactly like run_dense.cpp:391-400.
+  const char* hp = getenv("OFDIS_HOST_PYRAMID");
+  if (!(hp && atoi(hp))) {
+    if (verbosity > 1) printf("TIME (Image loading     ) (ms): %3g\n", elapsed_ms(tv));
+    ImageF out;
+    out.w = width_org;
+    out.h = height_org;
+    out.c = nop;
+    out.px.assign((size_t)out.w * out.h * nop, 0.f);
+    if (verbosity > 1) printf("TIME (Pyramide+Gradients) (ms): %3g\n", elapsed_ms(tv));  // inside the run below
+    try {
+      OFC::OFClass ofc(a8.px.data(), b8.px.data(), width_org, height_org, out.px.data(), nullptr, lv_f, lv_l, maxiter,
+                       miniter, mindprate, mindrrate, minimgerr, patchsz, poverl, usefbcon, costfct, nochannels,
+                       patnorm, usetvref, tv_alpha, tv_gamma, tv_delta, tv_innerit, tv_solverit, tv_sor, verbosity, nop);
+    } catch (const std::exception& e) {
+      fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
+    if (verbosity > 1) gettimeofday(&tv, NULL);
+    if (SELECTMODE == 1) SaveFlowFile(out, outfile);
+    else SavePFMFile(out, outfile);
+    if (verbosity > 1) printf("TIME (Saving flow file  ) (ms): %3g\n", elapsed_ms(tv));
+    return 0;
+  }
   ImageF img_ao_fmat = to_float(a8), img_bo_fmat = to_float(b8);
   const int szw = img_ao_fmat.w, szh = img_ao_fmat.h;
   if (verbosity > 1) printf("TIME (Image loading     ) (ms): %3g\n", elapsed_ms(tv));

@@ -88,6 +88,13 @@ def test_cli_output_equals_python_pipeline(tmp_path, bindir, oracle_port, exe, c
     out = str(tmp_path / ("out.flo" if nop == 2 else "out.pfm"))
     r = subprocess.run([os.path.join(bindir, exe), fa, fb, out] + args, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+    # same run with the pre/post-processing on the host (float pyramids handed to OFClass like the
+    # reference's main): the two outputs must be the same file
+    out_host = out + ".host"
+    r2 = subprocess.run([os.path.join(bindir, exe), fa, fb, out_host] + args, capture_output=True, text=True,
+                        env=dict(os.environ, OFDIS_HOST_PYRAMID="1"))
+    assert r2.returncode == 0, r2.stdout + r2.stderr
+    assert open(out, "rb").read() == open(out_host, "rb").read()
     if len(args) <= 1:
         assert "TIME (O.Flow Run-Time   ) (ms):" in r.stdout and "TIME (Sc:" in r.stdout  # verbosity 2 lines
         prm = params.operating_point(int(args[0]) if args else 2, w, noc=ch, nop=nop)

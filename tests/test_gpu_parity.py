@@ -315,3 +315,16 @@ def test_fullres_output_stage_equals_postprocess(nop, size, op, api):
         exp = preprocess.postprocess(ctx.get_flow(f, prm.sc_l), prm.sc_l, p.padw, p.padh, size[1], size[0])
         assert_bits(out[f], exp.reshape(out[f].shape), "frame %d" % f)
     ctx.close()
+
+
+def test_full_size_stereo_op4_vs_oracle(api, oracle_port):
+    """BASELINE configs[4]: run_DE_INT geometry, 2880x1988 (Middlebury shape), operating point 4
+    (P=12, 128 iterations, levels 6..1; level 1 has 994 rows -- the tall-level SOR variant)."""
+    prm = params.operating_point(4, 2880, noc=1, nop=1)
+    i0, i1, _ = synth.synthetic_pair(1988, 2880, 1, seed=4, amp=6.0, stereo=True)
+    pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
+    ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    ctx.upload_pyramids(0, pyr)
+    ctx.run(1)
+    assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "cfg5 run")
+    ctx.close()
