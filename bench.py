@@ -400,12 +400,23 @@ def main():
             g = ctx.level_info(lv)
             alg += prm.tv_innerit * (lv + 1) * 44 * g["w"] * g["h"] * B  # bytes, SURVEY 8(d)
         ach = alg / (sor["ms_per_step"] * 1e-3) / 1e9
-        traffic = None
+        traffic, issue = None, None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("sor_dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("sor_dram_bytes_per_launch")
+            # what actually bounds the overlapped step: warp-instruction issue.  ncu counts the warp
+            # instructions of one step (profiles/r1c_launches_step_b64.csv); an SM issues at most
+            # 4 per cycle.  Utilisation = instructions / (step time x SMs x 4 x SM clock).
+            wi = tj.get("warp_instructions_per_step")
+            if wi and B == 64 and clocks.get("sm_mhz"):
+                sms = torch.cuda.get_device_properties(local).multi_processor_count
+                issue = {"warp_instructions_per_step": wi, "sms": sms, "sm_mhz": clocks["sm_mhz"],
+                         "issue_slot_utilisation": wi / (ms_res * 1e-3 * sms * 4 * clocks["sm_mhz"] * 1e6),
+                         "ipc_per_sm": wi / (ms_res * 1e-3 * sms * clocks["sm_mhz"] * 1e6)}
         roof = {"bound": "hbm", "kernel": "sor_tma_kernel (lexicographic SOR wavefront, all sweeps fused; sor_kernel on levels that exceed its shared-memory budget)", "achieved": ach,
-                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": how,
+                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_note": "ncu dram bytes per SOR launch with caches flushed before every replay; "
+                "2.99e6 with --cache-control none (profiles/roofline_traffic.json)", "issue": issue, "peak_source": how,
                 "algorithmic_bytes_per_step": alg, "kernel_ms_per_step": sor["ms_per_step"],
                 "launches_per_step": sor["launches_per_step"],
                 "share_of_step": {k: v["ms_per_step"] for k, v in prof.items()}}
