@@ -138,41 +138,44 @@ __global__ void __launch_bounds__(256) deriv2_kernel(LevelGeom g, VarRefPlanes p
 // 2x2 inversion of sor_coupled's first sweep (solver.c:115-120).
 constexpr int TX = 32, TY = 8;
 
-template <int C, int NOP>
+// R rows per thread (tile 32 x 8R): the halo work of the two staging phases -- (TH+4)x36 flow
+// values and (TH+2)x34 smoothness weights per 32 x TH pixels -- shrinks from 1.69x / 1.33x (R=1)
+// to 1.27x / 1.13x (R=4).  All indices inside a frame are 32-bit.
+template <int C, int NOP, int R>
 __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp,
                                                              int f0, int first) {
-  __shared__ float2 s_uv[TY + 4][TX + 4];
-  __shared__ float s_s[TY + 2][TX + 2];
+  constexpr int TH = TY * R;
+  __shared__ float2 s_uv[TH + 4][TX + 4];
+  __shared__ float s_s[TH + 2][TX + 2];
   const int fr = blockIdx.z, frame = f0 + fr;
-  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TH;
   const int tid = threadIdx.y * TX + threadIdx.x;
   const int w = g.w, h = g.h, pitch = g.pitch;
-  const float* flow = g.flow + (size_t)frame * g.flow_frame_stride;
-  const float* dudv = reinterpret_cast<const float*>(pl.dudv + (size_t)fr * pl.dudv_stride);
+  const float* const flow = g.flow + (size_t)frame * g.flow_frame_stride;
+  const float* const dudv = reinterpret_cast<const float*>(pl.dudv + (size_t)fr * pl.dudv_stride);
   const int hpad = pl.hpad;
-  // (du,dv) of pixel (x,y) in the skewed layout: float4 0 of a block holds du x4, float4 1 dv x4
-  auto dudv_at = [&](int x, int y) -> float2 {
-    const size_t b = skew_f4(x >> 2, y, 0, 2, hpad) * 4 + (x & 3);
-    return make_float2(dudv[b], (NOP == 2) ? dudv[b + 4 * hpad] : 0.0f);
-  };
+  // float index of du of pixel (x,y) in the skewed layout (skew_f4 with NQ = 2): float4 0 of a
+  // block holds du x4, float4 1 (4*hpad floats on) dv x4
+  auto dudv_idx = [hpad](int x, int y) { return ((((x >> 2) + y) * 2) * hpad + y) * 4 + (x & 3); };
 
   // uu = wx + du (vv likewise); first iteration: uu = wx (refine_variational.cpp:189-190).
   // Coordinates are clamped, which also realises the replicate border of the 3-tap
   // horizontal derivative (image.c:448-454).
-  for (int idx = tid; idx < (TY + 4) * (TX + 4); idx += TX * TY) {
+  for (int idx = tid; idx < (TH + 4) * (TX + 4); idx += TX * TY) {
     const int cy = idx / (TX + 4), cx = idx - cy * (TX + 4);
     const int gx = clampi(x0 - 2 + cx, w), gy = clampi(y0 - 2 + cy, h);
-    const float* f = flow + ((size_t)gy * w + gx) * NOP;
+    const float* f = flow + (gy * w + gx) * NOP;
     float2 uv;
     uv.x = f[0];
     uv.y = (NOP == 2) ? f[1] : 0.0f;
     if (!first) {
-      const float2 d = dudv_at(gx, gy);
+      const int b = dudv_idx(gx, gy);
+      const float dx = dudv[b];
       if (NOP == 2) {
-        uv.x = uv.x + d.x;
-        uv.y = uv.y + d.y;
+        uv.x = uv.x + dx;
+        uv.y = uv.y + dudv[b + 4 * hpad];
       } else {  // minps / maxps with zero (refine_variational.cpp:299-314)
-        const float t = uv.x + d.x;
+        const float t = uv.x + dx;
         uv.x = (g.camlr == 0) ? (t < 0.0f ? t : 0.0f) : (t > 0.0f ? t : 0.0f);
       }
     }
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   // smoothness weight s = quarter_alpha / sqrt(ux^2+uy^2+vx^2+vy^2+eps) on the tile + 1 halo
   {
     const float c0 = -0.5f, c1 = -0.0f, c2 = 0.5f;  // {0,-0.5} -> [-0.5,-0,0.5]
-    for (int idx = tid; idx < (TY + 2) * (TX + 2); idx += TX * TY) {
+    for (int idx = tid; idx < (TH + 2) * (TX + 2); idx += TX * TY) {
       const int cy = idx / (TX + 2), cx = idx - cy * (TX + 2);
       const int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
       if (gx < 0 || gx >= w || gy < 0 || gy >= h) continue;
@@ -208,9 +211,17 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   }
   __syncthreads();
 
-  const int i = x0 + threadIdx.x, j = y0 + threadIdx.y;
-  if (i >= w || j >= h) return;
-  const int cx = threadIdx.x + 1, cy = threadIdx.y + 1;
+  const int i = x0 + threadIdx.x;
+  if (i >= w) return;
+  const float hdo3 = vp.half_delta_over3, hgo3 = vp.half_gamma_over3;
+  const float* const maskp = pl.mask + (size_t)fr * pl.plane;
+  float* const rec = reinterpret_cast<float*>(pl.rec + (size_t)fr * pl.rec_stride);
+  const int fs = hpad * 4;  // floats between consecutive record fields of a block
+#pragma unroll 1
+  for (int rr = 0; rr < R; ++rr) {
+  const int ly = threadIdx.y + TY * rr, j = y0 + ly;
+  if (j >= h) break;
+  const int cx = threadIdx.x + 1, cy = ly + 1;
   const float sc = s_s[cy][cx];
   const float hh = (i < w - 1) ? sc + s_s[cy][cx + 1] : 0.0f;    // sh(i,j)   (opticalflow_aux.c:150-154)
   const float hl = (i > 0) ? s_s[cy][cx - 1] + sc : 0.0f;        // sh(i-1,j)
@@ -218,10 +229,9 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   const float vt = (j > 0) ? s_s[cy - 1][cx] + sc : 0.0f;        // sv(i,j-1)
 
   const int o = j * pitch + i;
-  const float m = pl.mask[(size_t)fr * pl.plane + o];
-  const float2 d = dudv_at(i, j);
-  const float u = d.x, v = (NOP == 2) ? d.y : 0.0f;
-  const float hdo3 = vp.half_delta_over3, hgo3 = vp.half_gamma_over3;
+  const float m = maskp[o];
+  const int db = dudv_idx(i, j);
+  const float u = dudv[db], v = (NOP == 2) ? dudv[db + 4 * hpad] : 0.0f;
   float A11 = 0.f, A12 = 0.f, A22 = 0.f, B1 = 0.f, B2 = 0.f;
 #define DRV(k, c) pl.deriv[k][((size_t)fr * C + (c)) * pl.plane + o]
   if (C == 1) {
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
 
   // sub_laplacian (opticalflow_aux.c:172-199), per-pixel order -h(i-1) +h(i) -v(j-1) +v(j)
   {
-    const float* fc = flow + ((size_t)j * w + i) * NOP;
+    const float* fc = flow + (j * w + i) * NOP;
     const float wxc = fc[0];
     if (i > 0) B1 -= hl * (wxc - fc[-NOP]);
     if (i < w - 1) B1 += hh * (fc[NOP] - wxc);
@@ -339,8 +349,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     const float det = iA11 * iA22 - A12 * A12;
     // record of the 4-pixel block, SoA: float4 f of the block holds field f of its 4 pixels;
     // fields: a11^-1, a12^-1, a22^-1, b1, b2, sh, sv, sv(row above)
-    float* rec = reinterpret_cast<float*>(pl.rec + (size_t)fr * pl.rec_stride);
-    const size_t b0 = skew_f4(i >> 2, j, 0, 8, hpad) * 4 + (i & 3), fs = (size_t)hpad * 4;
+    const int b0 = (((i >> 2) + j) * 8 * hpad + j) * 4 + (i & 3);  // skew_f4(I, j, 0, 8, hpad)
     rec[b0] = iA11 / det;
     rec[b0 + fs] = A12 / -det;
     rec[b0 + 2 * fs] = iA22 / det;
@@ -357,14 +366,14 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     if (j < h - 1) sum += vv;
     if (i < w - 1) sum += hh;
     // stereo record fields: A11 = a11 + sum, b1, sh, sv, sv(row above)
-    float* rec = reinterpret_cast<float*>(pl.rec + (size_t)fr * pl.rec_stride);
-    const size_t b0 = skew_f4(i >> 2, j, 0, 5, hpad) * 4 + (i & 3), fs = (size_t)hpad * 4;
+    const int b0 = (((i >> 2) + j) * 5 * hpad + j) * 4 + (i & 3);  // skew_f4(I, j, 0, 5, hpad)
     rec[b0] = A11 + sum;
     rec[b0 + fs] = B1;
     rec[b0 + 2 * fs] = hh;
     rec[b0 + 3 * fs] = vv;
     rec[b0 + 4 * fs] = vt;
   }
+  }  // rows of this thread
 }
 
 // ---------------------------------------------------------------------------
@@ -612,6 +621,11 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   const int nf = f1 - f0;
   const dim3 block(TX, TY), grid((g.w + TX - 1) / TX, (g.h + TY - 1) / TY, nf);
   const dim3 gridc(grid.x, grid.y, nf * C);
+  // assemble_kernel: as many rows per thread (less halo work) as still leave >= 256 CTAs
+  int rows_per_thread = 1;
+  for (int r = 4; r > 1; r >>= 1)
+    if ((long)grid.x * ((g.h + TY * r - 1) / (TY * r)) * nf >= 256) { rows_per_thread = r; break; }
+  const dim3 grid_a(grid.x, (g.h + TY * rows_per_thread - 1) / (TY * rows_per_thread), nf);
   {
     ProfScope scope(prof, KC_VR_SETUP);
     warp_kernel<C, NOP><<<grid, block, 0, st>>>(g, pl, f0);
@@ -662,7 +676,9 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   for (int it = 0; it < vp.n_inner; ++it) {
     {
       ProfScope scope(prof, KC_VR_ASSEMBLE);
-      assemble_kernel<C, NOP><<<grid, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
+      if (rows_per_thread == 4) assemble_kernel<C, NOP, 4><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
+      else if (rows_per_thread == 2) assemble_kernel<C, NOP, 2><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
+      else assemble_kernel<C, NOP, 1><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
     }
     ++launches;
     if (use_tma) {
