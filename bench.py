@@ -126,11 +126,12 @@ def cpu_reference_mpix(prm, pyrs, seconds, threads):
         port_driver.build()
     fn(pyrs[0], prm)  # warm
     done = 0
+    work = [pyrs[i % len(pyrs)] for i in range(max(len(pyrs), threads))]  # at least one pair per thread
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
         while time.perf_counter() - t0 < seconds:
-            list(ex.map(lambda p: fn(p, prm), pyrs))
-            done += len(pyrs)
+            list(ex.map(lambda p: fn(p, prm), work))
+            done += len(work)
     dt = time.perf_counter() - t0
     return done * H_ORG * W_ORG / dt / 1e6, kind, done
 
@@ -139,9 +140,12 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    npairs = args.batch * world
-    threads = min(cores, npairs)
-    prm, pyrs = make_pairs(npairs, 0)
+    # one step = the arm's batch, enlarged to one pair per hardware thread when the batch is smaller
+    # (the reference is single-threaded per pair; frame parallelism is the only way it uses the host)
+    npairs = max(args.batch * world, cores)
+    threads = cores
+    prm, pyrs0 = make_pairs(min(npairs, args.batch * world), 0)
+    pyrs = [pyrs0[i % len(pyrs0)] for i in range(npairs)]
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import port_driver, ref_driver
@@ -450,7 +454,7 @@ def main():
 
     numa.unbind(prev_affinity)  # the CPU baseline uses every core of the host
     cores = os.cpu_count() or 1
-    threads = min(cores, B)
+    threads = cores
     cpu_val, kind, done = cpu_reference_mpix(prm, pyrs, args.cpu_seconds, threads) if world == 1 else (None, None, 0)
     line = {
         "metric": "Mpix/s dense flow (1024x436, op-point 2)", "value": value, "unit": "Mpix/s", "n_gpus": world,

@@ -70,6 +70,8 @@ def build_host(force: bool = False) -> str:
     link = ["-L" + LIBDIR, "-lofdis_b200", "-lz", "-Wl,-rpath,$ORIGIN/../lib"]
     jobs = {name: common + [os.path.join(HOST, "run_dense.cpp"), "-DSELECTMODE=%d" % m, "-DSELECTCHANNEL=%d" % c]
             for name, (m, c) in CLI_TARGETS.items()}
+    for name, (m, c) in CLI_TARGETS.items():  # batch front-end: list file in, many pairs per launch
+        jobs[name + "_batch"] = jobs[name] + ["-DOFDIS_BATCH"]
     jobs["ofdis_host_selftest"] = common + [os.path.join(HOST, "host_selftest.cpp")]
     for name, cmd in jobs.items():
         out = os.path.join(BINDIR, name)

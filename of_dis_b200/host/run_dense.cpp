@@ -336,6 +336,49 @@ void SavePFMFile(const ImageF& img, const char* filename) {
   fclose(stream);
 }
 
+// Parameter block of the command line: nothing, one operating-point digit, or the 20 explicit
+// numbers (run_dense.cpp:219-294, README.md:66-88).
+struct CliParams {
+  int lv_f, lv_l, maxiter, miniter, patchsz, patnorm, costfct, tv_innerit, tv_solverit, verbosity;
+  float mindprate, mindrrate, minimgerr, poverl, tv_alpha, tv_gamma, tv_delta, tv_sor;
+  bool usefbcon, usetvref;
+};
+
+void parse_cli_params(int nnum, char** num, int width_org, CliParams& P) {
+  if (nnum <= 1) {
+    P.mindprate = 0.05; P.mindrrate = 0.95; P.minimgerr = 0.0;
+    P.usefbcon = 0; P.patnorm = 1; P.costfct = 0;
+    P.tv_alpha = 10.0; P.tv_gamma = 10.0; P.tv_delta = 5.0;
+    P.tv_innerit = 1; P.tv_solverit = 3; P.tv_sor = 1.6;
+    P.verbosity = 2;
+    const int fratio = 5;
+    int sel_oppoint = 2;
+    if (nnum == 1) sel_oppoint = atoi(num[0]);
+    switch (sel_oppoint) {
+      case 1: P.patchsz = 8; P.poverl = 0.3; P.lv_f = AutoFirstScaleSelect(width_org, fratio, P.patchsz);
+        P.lv_l = std::max(P.lv_f - 2, 0); P.maxiter = 16; P.miniter = 16; P.usetvref = 0; break;
+      case 3: P.patchsz = 12; P.poverl = 0.75; P.lv_f = AutoFirstScaleSelect(width_org, fratio, P.patchsz);
+        P.lv_l = std::max(P.lv_f - 4, 0); P.maxiter = 16; P.miniter = 16; P.usetvref = 1; break;
+      case 4: P.patchsz = 12; P.poverl = 0.75; P.lv_f = AutoFirstScaleSelect(width_org, fratio, P.patchsz);
+        P.lv_l = std::max(P.lv_f - 5, 0); P.maxiter = 128; P.miniter = 128; P.usetvref = 1; break;
+      case 2:
+      default: P.patchsz = 8; P.poverl = 0.4; P.lv_f = AutoFirstScaleSelect(width_org, fratio, P.patchsz);
+        P.lv_l = std::max(P.lv_f - 2, 0); P.maxiter = 12; P.miniter = 12; P.usetvref = 1; break;
+    }
+  } else {
+    int acnt = 0;
+    P.lv_f = atoi(num[acnt++]); P.lv_l = atoi(num[acnt++]);
+    P.maxiter = atoi(num[acnt++]); P.miniter = atoi(num[acnt++]);
+    P.mindprate = atof(num[acnt++]); P.mindrrate = atof(num[acnt++]); P.minimgerr = atof(num[acnt++]);
+    P.patchsz = atoi(num[acnt++]); P.poverl = atof(num[acnt++]);
+    P.usefbcon = atoi(num[acnt++]); P.patnorm = atoi(num[acnt++]); P.costfct = atoi(num[acnt++]);
+    P.usetvref = atoi(num[acnt++]);
+    P.tv_alpha = atof(num[acnt++]); P.tv_gamma = atof(num[acnt++]); P.tv_delta = atof(num[acnt++]);
+    P.tv_innerit = atoi(num[acnt++]); P.tv_solverit = atoi(num[acnt++]); P.tv_sor = atof(num[acnt++]);
+    P.verbosity = atoi(num[acnt++]);
+  }
+}
+
 double elapsed_ms(timeval& a) {
   timeval b;
   gettimeofday(&b, NULL);
@@ -346,6 +389,122 @@ double elapsed_ms(timeval& a) {
 
 }  // namespace
 
+#ifdef OFDIS_BATCH
+// Batch front-end: many pairs per launch through the C-ABI's frame dimension.
+//
+//   run_*_*_batch listfile [--batch N] [oppoint | p1 .. p20]
+//
+// listfile: one "image1 image2 outputfile" triple per line.  Consecutive pairs of the same size are
+// grouped into batches of up to N (default 64): 8-bit frames up, pyramid / hot path / upsampling
+// on the device, full-resolution flows back.  Every output is byte-identical to what the
+// single-pair binary writes for that pair.
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    fprintf(stderr, "usage: %s listfile [--batch N] [oppoint | 20 parameters (README.md:66-88)]\n", argv[0]);
+    return 2;
+  }
+  int maxb = 64, first_num = 2;
+  if (argc >= 4 && !strcmp(argv[2], "--batch")) {
+    maxb = atoi(argv[3]);
+    first_num = 4;
+  }
+  const int nnum = argc - first_num;
+  if (maxb < 1 || (nnum > 1 && nnum != 20)) {
+    fprintf(stderr, "error: expected 0, 1 or exactly 20 numbers, got %d\n", nnum);
+    return 2;
+  }
+  struct Job { string a, b, out; };
+  vector<Job> jobs;
+  {
+    FILE* f = fopen(argv[1], "r");
+    if (!f) {
+      fprintf(stderr, "error: cannot read %s\n", argv[1]);
+      return 1;
+    }
+    char a[4096], b[4096], o[4096];
+    while (fscanf(f, "%4095s %4095s %4095s", a, b, o) == 3) jobs.push_back({a, b, o});
+    fclose(f);
+  }
+  const int nochannels = (SELECTCHANNEL == 3) ? 3 : 1;
+  const int nop = (SELECTMODE == 1) ? 2 : 1;
+  timeval tv;
+  gettimeofday(&tv, NULL);
+  size_t done = 0;
+  ofdis_ctx* ctx = nullptr;
+  int ctx_w = -1, ctx_h = -1, verbosity = 0;
+  vector<uint8_t> frames;
+  vector<float> flows;
+  size_t j0 = 0;
+  while (j0 < jobs.size()) {
+    // load up to maxb pairs of one size
+    Image8 a8, b8;
+    int w = 0, h = 0, n = 0;
+    frames.clear();
+    while (j0 + n < jobs.size() && n < maxb) {
+      const Job& jb = jobs[j0 + n];
+      if (!load_image(jb.a.c_str(), nochannels, a8) || !load_image(jb.b.c_str(), nochannels, b8) || a8.w != b8.w ||
+          a8.h != b8.h) {
+        fprintf(stderr, "error: cannot read the pair %s %s (binary PGM/PPM or 8-bit PNG of equal size)\n",
+                jb.a.c_str(), jb.b.c_str());
+        if (ctx) ofdis_destroy(ctx);
+        return 1;
+      }
+      if (n == 0) { w = a8.w; h = a8.h; }
+      else if (a8.w != w || a8.h != h) break;  // next group
+      frames.insert(frames.end(), a8.px.begin(), a8.px.end());
+      frames.insert(frames.end(), b8.px.begin(), b8.px.end());
+      ++n;
+    }
+    CliParams P;
+    parse_cli_params(nnum, argv + first_num, w, P);
+    verbosity = P.verbosity;
+    if (w != ctx_w || h != ctx_h) {
+      if (ctx) ofdis_destroy(ctx);
+      ctx = nullptr;
+      ofdis_params p;
+      memset(&p, 0, sizeof(p));
+      p.sc_f = P.lv_f; p.sc_l = P.lv_l; p.max_iter = P.maxiter; p.min_iter = P.miniter;
+      p.dp_thresh = P.mindprate; p.dr_thresh = P.mindrrate; p.res_thresh = P.minimgerr;
+      p.p_samp_s = P.patchsz; p.patove = P.poverl; p.usefbcon = P.usefbcon ? 1 : 0; p.costfct = P.costfct;
+      p.noc = nochannels; p.patnorm = P.patnorm; p.usetvref = P.usetvref ? 1 : 0;
+      p.tv_alpha = P.tv_alpha; p.tv_gamma = P.tv_gamma; p.tv_delta = P.tv_delta;
+      p.tv_innerit = P.tv_innerit; p.tv_solverit = P.tv_solverit; p.tv_sor = P.tv_sor; p.verbosity = P.verbosity;
+      const int scf = 1 << P.lv_f;
+      const int rc = ofdis_create(&ctx, 0, nullptr, &p, nop, (w + scf - 1) / scf * scf, (h + scf - 1) / scf * scf,
+                                  P.patchsz, maxb);
+      if (rc != OFDIS_OK) {
+        fprintf(stderr, "error: ofdis_create failed with status %d for %dx%d frames\n", rc, w, h);
+        return 1;
+      }
+      ofdis_set_graph_mode(ctx, 1);
+      ctx_w = w;
+      ctx_h = h;
+    }
+    flows.resize((size_t)n * w * h * nop);
+    int rc = ofdis_upload_frames_u8(ctx, 0, n, frames.data(), w, h, OFDIS_MEM_HOST);
+    if (rc == OFDIS_OK) rc = ofdis_run(ctx, n, 0);
+    if (rc == OFDIS_OK) rc = ofdis_get_flow_fullres(ctx, 0, n, flows.data(), w, h, OFDIS_MEM_HOST);
+    if (rc == OFDIS_OK) rc = ofdis_sync(ctx);
+    if (rc != OFDIS_OK) {
+      fprintf(stderr, "error: %s\n", ofdis_last_error(ctx));
+      ofdis_destroy(ctx);
+      return 1;
+    }
+    ImageF out;
+    out.w = w; out.h = h; out.c = nop;
+    for (int k = 0; k < n; ++k) {
+      out.px.assign(flows.begin() + (size_t)k * w * h * nop, flows.begin() + (size_t)(k + 1) * w * h * nop);
+      if (SELECTMODE == 1) SaveFlowFile(out, jobs[j0 + k].out.c_str());
+      else SavePFMFile(out, jobs[j0 + k].out.c_str());
+    }
+    j0 += n;
+    done += n;
+  }
+  if (ctx) ofdis_destroy(ctx);
+  if (verbosity > 0) printf("TIME (%zu pairs, load + flow + save) (ms): %3g\n", done, elapsed_ms(tv));
+  return 0;
+}
+#else
 int main(int argc, char** argv) {
   timeval tv;
   gettimeofday(&tv, NULL);
@@ -372,41 +531,14 @@ int main(int argc, char** argv) {
   const int width_org = a8.w, height_org = a8.h;
 
   // *** parameters (run_dense.cpp:219-294)
-  int lv_f, lv_l, maxiter, miniter, patchsz, patnorm, costfct, tv_innerit, tv_solverit, verbosity;
-  float mindprate, mindrrate, minimgerr, poverl, tv_alpha, tv_gamma, tv_delta, tv_sor;
-  bool usefbcon, usetvref;
-  if (argc <= 5) {
-    mindprate = 0.05; mindrrate = 0.95; minimgerr = 0.0;
-    usefbcon = 0; patnorm = 1; costfct = 0;
-    tv_alpha = 10.0; tv_gamma = 10.0; tv_delta = 5.0;
-    tv_innerit = 1; tv_solverit = 3; tv_sor = 1.6;
-    verbosity = 2;
-    const int fratio = 5;
-    int sel_oppoint = 2;
-    if (argc == 5) sel_oppoint = atoi(argv[4]);
-    switch (sel_oppoint) {
-      case 1: patchsz = 8; poverl = 0.3; lv_f = AutoFirstScaleSelect(width_org, fratio, patchsz);
-        lv_l = std::max(lv_f - 2, 0); maxiter = 16; miniter = 16; usetvref = 0; break;
-      case 3: patchsz = 12; poverl = 0.75; lv_f = AutoFirstScaleSelect(width_org, fratio, patchsz);
-        lv_l = std::max(lv_f - 4, 0); maxiter = 16; miniter = 16; usetvref = 1; break;
-      case 4: patchsz = 12; poverl = 0.75; lv_f = AutoFirstScaleSelect(width_org, fratio, patchsz);
-        lv_l = std::max(lv_f - 5, 0); maxiter = 128; miniter = 128; usetvref = 1; break;
-      case 2:
-      default: patchsz = 8; poverl = 0.4; lv_f = AutoFirstScaleSelect(width_org, fratio, patchsz);
-        lv_l = std::max(lv_f - 2, 0); maxiter = 12; miniter = 12; usetvref = 1; break;
-    }
-  } else {
-    int acnt = 4;
-    lv_f = atoi(argv[acnt++]); lv_l = atoi(argv[acnt++]);
-    maxiter = atoi(argv[acnt++]); miniter = atoi(argv[acnt++]);
-    mindprate = atof(argv[acnt++]); mindrrate = atof(argv[acnt++]); minimgerr = atof(argv[acnt++]);
-    patchsz = atoi(argv[acnt++]); poverl = atof(argv[acnt++]);
-    usefbcon = atoi(argv[acnt++]); patnorm = atoi(argv[acnt++]); costfct = atoi(argv[acnt++]);
-    usetvref = atoi(argv[acnt++]);
-    tv_alpha = atof(argv[acnt++]); tv_gamma = atof(argv[acnt++]); tv_delta = atof(argv[acnt++]);
-    tv_innerit = atoi(argv[acnt++]); tv_solverit = atoi(argv[acnt++]); tv_sor = atof(argv[acnt++]);
-    verbosity = atoi(argv[acnt++]);
-  }
+  CliParams P;
+  parse_cli_params(argc - 4, argv + 4, width_org, P);
+  const int lv_f = P.lv_f, lv_l = P.lv_l, maxiter = P.maxiter, miniter = P.miniter, patchsz = P.patchsz,
+            patnorm = P.patnorm, costfct = P.costfct, tv_innerit = P.tv_innerit, tv_solverit = P.tv_solverit,
+            verbosity = P.verbosity;
+  const float mindprate = P.mindprate, mindrrate = P.mindrrate, minimgerr = P.minimgerr, poverl = P.poverl,
+              tv_alpha = P.tv_alpha, tv_gamma = P.tv_gamma, tv_delta = P.tv_delta, tv_sor = P.tv_sor;
+  const bool usefbcon = P.usefbcon, usetvref = P.usetvref;
 
   // *** pad so that width/height are divisible by 2^lv_f (run_dense.cpp:298-311)
   int padw = 0, padh = 0;
@@ -499,3 +631,4 @@ int main(int argc, char** argv) {
   if (verbosity > 1) printf("TIME (Saving flow file  ) (ms): %3g\n", elapsed_ms(tv));
   return 0;
 }
+#endif  // OFDIS_BATCH

@@ -113,3 +113,36 @@ def test_cli_output_equals_python_pipeline(tmp_path, bindir, oracle_port, exe, c
     assert got.shape == exp.shape
     assert np.array_equal(np.ascontiguousarray(got).view(np.uint32), np.ascontiguousarray(exp).view(np.uint32)), \
         float(np.abs(got - exp).max())
+
+
+def test_batch_front_end_usage(bindir):
+    exe = os.path.join(bindir, "run_OF_INT_batch")
+    assert subprocess.run([exe], capture_output=True).returncode == 2
+    r = subprocess.run([exe, "/nonexistent/list.txt"], capture_output=True)
+    assert r.returncode == 1
+    r = subprocess.run([exe, "/nonexistent/list.txt", "1", "2", "3"], capture_output=True)
+    assert r.returncode == 2 and b"20" in r.stderr
+
+
+@pytest.mark.gpu
+def test_batch_front_end_writes_the_files_of_the_single_pair_binary(tmp_path, bindir):
+    """run_OF_INT_batch (list file, pairs grouped by size, many pairs per launch) == run_OF_INT per pair."""
+    sizes = [(218, 500), (218, 500), (218, 500), (150, 250), (150, 250)]
+    lines, singles = [], []
+    for k, (h, w) in enumerate(sizes):
+        i0, i1, _ = synth.synthetic_pair(h, w, 1, seed=40 + k)
+        fa, fb = str(tmp_path / ("a%d.pgm" % k)), str(tmp_path / ("b%d.pgm" % k))
+        write_pnm(fa, i0)
+        write_pnm(fb, i1)
+        lines.append("%s %s %s" % (fa, fb, tmp_path / ("batch%d.flo" % k)))
+        singles.append((fa, fb, str(tmp_path / ("single%d.flo" % k))))
+    lst = tmp_path / "list.txt"
+    lst.write_text("\n".join(lines) + "\n")
+    r = subprocess.run([os.path.join(bindir, "run_OF_INT_batch"), str(lst), "--batch", "2", "2"], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "5 pairs" in r.stdout
+    for k, (fa, fb, out) in enumerate(singles):
+        r = subprocess.run([os.path.join(bindir, "run_OF_INT"), fa, fb, out, "2"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert open(out, "rb").read() == open(str(tmp_path / ("batch%d.flo" % k)), "rb").read(), k
