@@ -733,31 +733,154 @@ void dis_varref_level(const dis_level* L, const dis_params* prm, const float* i0
   free(buf);
 }
 
-/* OFClass::OFClass level loop (oflow.cpp:184-295), usefbcon == 0 */
-int dis_run(const float** i0, const float** i0x, const float** i0y, const float** i1, int pad,
-            float* outflow, const float* initflow, int width, int height, const dis_params* prm,
-            int nop) {
-  float* prev = NULL;
+/* The second loop of PatGridClass::AggregateFlowDense (patchgrid.cpp:278-375): the complementary
+ * grid's patches, at their displaced positions, splat their NEGATED flow bilinearly.  Gather form:
+ * for one cell the reference's scatter visits the patches in ascending ip and, inside a patch, the
+ * pixels in raster order, so a cell receives at most four terms per patch -- from the patch pixels
+ * at (cx,cy) [weight wbil0], (cx+1,cy) [wbil1], (cx,cy+1) [wbil2], (cx+1,cy+1) [wbil3], in that order. */
+static void densify_cg_cell(const dis_level* L, const float* cg_p, const float* cg_pweight, int xi, int yi,
+                            float* we, float* acc) {
+  const int P = L->P, C = L->noc, n = C * P * P, nop = L->nop, lb = -P / 2, ub = P / 2 - 1;
+  const float minerrval = 2.0f;
+  int px, py, t, c, k;
+  for (px = 0; px < L->nopw; ++px)
+    for (py = 0; py < L->noph; ++py) {
+      const int ip = px * L->noph + py;
+      const float refx = (float)(px * L->steps + L->offw), refy = (float)(py * L->steps + L->offh);
+      /* GetPointPos() == pt_iter == pt_ref + p_iter (patch.cpp:214-221; stereo keeps the row) */
+      const float rpx = refx + cg_p[ip * nop], rpy = (nop == 2) ? refy + cg_p[ip * nop + 1] : refy;
+      const int pos0 = (int)ceil(rpx + .00001), pos1 = (int)ceil(rpy + .00001); /* double literal: patchgrid.cpp:308-309 */
+      const int pos2 = (int)floorf(rpx), pos3 = (int)floorf(rpy);
+      float wbil[4], r0, r1;
+      int x0, x1, y0;
+      if (xi < pos0 + lb - 1 || xi > pos0 + ub || yi < pos1 + lb - 1 || yi > pos1 + ub) continue;
+      r0 = rpx - pos2;
+      r1 = rpy - pos3;
+      wbil[0] = r0 * r1;
+      wbil[1] = (1 - r0) * r1;
+      wbil[2] = r0 * (1 - r1);
+      wbil[3] = (1 - r0) * (1 - r1);
+      /* in-image rectangle of this patch (the reference's test xt>=1, yt>=1, xt<w-1, yt<h-1), patch coordinates */
+      x0 = 1 - pos0 - lb; if (x0 < 0) x0 = 0;
+      x1 = L->w - 2 - pos0 - lb; if (x1 > P - 1) x1 = P - 1;
+      y0 = 1 - pos1 - lb; if (y0 < 0) y0 = 0;
+      for (t = 0; t < 4; ++t) {
+        const int xt = xi + (t & 1), yt = yi + (t >> 1);
+        const int rx = xt - pos0 - lb, ry = yt - pos1 - lb; /* pixel inside the patch, 0..P-1 */
+        const float* pw;
+        float absw;
+        if (rx < 0 || rx > P - 1 || ry < 0 || ry > P - 1) continue;
+        if (!(xt >= 1 && yt >= 1 && xt < L->w - 1 && yt < L->h - 1)) continue;
+        /* weight cursor: +1 per pixel, +(C-1) more per in-image pixel before this one (patchgrid.cpp:331-339) */
+        pw = cg_pweight + (size_t)ip * n + (ry * P + rx) + (C - 1) * ((ry - y0) * (x1 - x0 + 1) + (rx - x0));
+        if (C == 1)
+          absw = 1.0f / STD_MAX(minerrval, pw[0]);
+        else {
+          absw = STD_MAX(minerrval, pw[0]);
+          for (c = 1; c < C; ++c) absw += STD_MAX(minerrval, pw[c]);
+          absw = 1.0f / absw;
+        }
+        *we += wbil[t] * absw;
+        for (k = 0; k < nop; ++k) acc[k] -= wbil[t] * (cg_p[ip * nop + k] * absw);
+      }
+    }
+}
+
+/* AggregateFlowDense with the forward-backward merge (usefbcon): own patches, then the
+ * complementary grid's, then the normalisation (patchgrid.cpp:213-394). */
+void dis_densify_fb(const dis_level* L, const dis_params* prm, const float* p, const float* pweight,
+                    const float* cg_p, const float* cg_pweight, float* flow_out) {
+  const int P = L->P, C = L->noc, n = C * P * P, nop = L->nop;
+  const float minerrval = 2.0f;
+  int xi, yi, px, py, c, k;
+  (void)prm;
+  for (yi = 0; yi < L->h; ++yi)
+    for (xi = 0; xi < L->w; ++xi) {
+      float we = 0, acc[2] = {0, 0};
+      for (px = 0; px < L->nopw; ++px) {
+        int dx = xi - (px * L->steps + L->offw);
+        if (dx < -P / 2 || dx > P / 2 - 1) continue;
+        for (py = 0; py < L->noph; ++py) {
+          int dy = yi - (py * L->steps + L->offh), ip = px * L->noph + py;
+          const float* pw;
+          float absw;
+          if (dy < -P / 2 || dy > P / 2 - 1) continue;
+          {
+            int rx = dx + P / 2, ry = dy + P / 2, cx = px * L->steps + L->offw, cy = py * L->steps + L->offh;
+            int x0 = cx - P / 2 < 0 ? P / 2 - cx : 0, y0 = cy - P / 2 < 0 ? P / 2 - cy : 0;
+            int x1 = cx + P / 2 - 1 > L->w - 1 ? L->w - 1 - cx + P / 2 : P - 1;
+            int inb = (ry - y0) * (x1 - x0 + 1) + (rx - x0);
+            pw = pweight + (size_t)ip * n + (ry * P + rx) + (C - 1) * inb;
+          }
+          if (C == 1)
+            absw = 1.0f / STD_MAX(minerrval, pw[0]);
+          else {
+            absw = STD_MAX(minerrval, pw[0]);
+            for (c = 1; c < C; ++c) absw += STD_MAX(minerrval, pw[c]);
+            absw = 1.0f / absw;
+          }
+          we += absw;
+          for (k = 0; k < nop; ++k) acc[k] += p[ip * nop + k] * absw;
+        }
+      }
+      if (cg_p) densify_cg_cell(L, cg_p, cg_pweight, xi, yi, &we, acc);
+      for (k = 0; k < nop; ++k) flow_out[(yi * L->w + xi) * nop + k] = we > 0 ? acc[k] / we : acc[k];
+    }
+}
+
+/* OFClass::OFClass level loop (oflow.cpp:184-295) including the forward-backward variant:
+ * a second grid on the swapped images (camlr = 1), merged at every densification; the backward
+ * flow is densified and refined on all but the last level. */
+int dis_run_fb(const float** i0, const float** i0x, const float** i0y, const float** i1, const float** i1x,
+               const float** i1y, int pad, float* outflow, const float* initflow, int width, int height,
+               const dis_params* prm, int nop) {
+  float *prev = NULL, *prev_bw = NULL;
+  const int fb = prm->usefbcon != 0;
   int sl;
-  if (prm->usefbcon) return -1;
+  if (fb && (!i1x || !i1y)) return -1;
   for (sl = prm->sc_f; sl >= prm->sc_l; --sl) {
-    dis_level L;
+    dis_level L, Lb;
     int np, n;
-    float *p, *pw, *cur;
+    float *p, *pw, *cur, *pb = NULL, *pwb = NULL, *cur_bw = NULL;
     dis_make_level(&L, width, height, sl, pad, prm, nop, 0);
+    dis_make_level(&Lb, width, height, sl, pad, prm, nop, 1);
     np = L.nopw * L.noph;
     n = L.noc * L.P * L.P;
     p = (float*)malloc(sizeof(float) * np * nop);
     pw = (float*)malloc(sizeof(float) * (size_t)np * n);
     cur = (sl == prm->sc_l) ? outflow : (float*)malloc(sizeof(float) * L.w * L.h * nop);
-    dis_patches_level(&L, prm, i0[sl], i0x[sl], i0y[sl], i1[sl],
-                      sl < prm->sc_f ? prev : initflow, p, pw, NULL, NULL);
-    dis_densify(&L, prm, p, pw, cur);
-    if (prm->usetvref) dis_varref_level(&L, prm, i0[sl], i1[sl], cur);
+    dis_patches_level(&L, prm, i0[sl], i0x[sl], i0y[sl], i1[sl], sl < prm->sc_f ? prev : initflow, p, pw, NULL, NULL);
+    if (fb) {
+      pb = (float*)malloc(sizeof(float) * np * nop);
+      pwb = (float*)malloc(sizeof(float) * (size_t)np * n);
+      dis_patches_level(&Lb, prm, i1[sl], i1x[sl], i1y[sl], i0[sl], sl < prm->sc_f ? prev_bw : NULL, pb, pwb, NULL,
+                        NULL);
+    }
+    dis_densify_fb(&L, prm, p, pw, pb, pwb, cur);
+    if (fb && sl > prm->sc_l) {
+      cur_bw = (float*)malloc(sizeof(float) * L.w * L.h * nop);
+      dis_densify_fb(&Lb, prm, pb, pwb, p, pw, cur_bw);
+    }
+    if (prm->usetvref) {
+      dis_varref_level(&L, prm, i0[sl], i1[sl], cur);
+      if (cur_bw) dis_varref_level(&Lb, prm, i1[sl], i0[sl], cur_bw);
+    }
     free(p);
     free(pw);
+    free(pb);
+    free(pwb);
     free(prev);
+    free(prev_bw);
     prev = (sl == prm->sc_l) ? NULL : cur;
+    prev_bw = cur_bw;
   }
+  free(prev_bw);
   return 0;
+}
+
+int dis_run(const float** i0, const float** i0x, const float** i0y, const float** i1, int pad,
+            float* outflow, const float* initflow, int width, int height, const dis_params* prm,
+            int nop) {
+  if (prm->usefbcon) return -1; /* needs the gradients of the second image: dis_run_fb */
+  return dis_run_fb(i0, i0x, i0y, i1, NULL, NULL, pad, outflow, initflow, width, height, prm, nop);
 }

@@ -76,6 +76,16 @@ void dis_sor_de(int w, int h, float* du, const float* a11, const float* b1, cons
 void dis_varref_level(const dis_level* L, const dis_params* prm, const float* i0, const float* i1,
                       float* flow);
 
+/* K4 with the forward-backward merge (patchgrid.cpp:213-394): cg_p / cg_pweight are the complementary
+ * grid's results (NULL: no merge, == dis_densify). */
+void dis_densify_fb(const dis_level* L, const dis_params* prm, const float* p, const float* pweight,
+                    const float* cg_p, const float* cg_pweight, float* flow_out);
+
+/* Whole run including usefbcon (second grid on the swapped images; needs i1x, i1y). */
+int dis_run_fb(const float** i0, const float** i0x, const float** i0y, const float** i1, const float** i1x,
+               const float** i1y, int pad, float* outflow, const float* initflow, int width, int height,
+               const dis_params* prm, int nop);
+
 /* Whole coarse-to-fine run == OFClass ctor (oflow.cpp:32-363), usefbcon must be 0. */
 int dis_run(const float** i0, const float** i0x, const float** i0y, const float** i1, int pad,
             float* outflow, const float* initflow, int width, int height, const dis_params* prm,

@@ -100,9 +100,9 @@ def port_run(pyr, prm, initflow=None) -> np.ndarray:
     h, w = pyr.level_shape(prm.sc_l)
     out = np.zeros((h, w, prm.nop), np.float32)
     cp = prm.to_c()
-    rc = lib().dis_run(_pyr_ptrs(pyr.i0), _pyr_ptrs(pyr.i0x), _pyr_ptrs(pyr.i0y), _pyr_ptrs(pyr.i1),
-                       pyr.imgpadding, _fp(out), _fp(initflow), pyr.width, pyr.height, ctypes.byref(cp),
-                       prm.nop)
+    rc = lib().dis_run_fb(_pyr_ptrs(pyr.i0), _pyr_ptrs(pyr.i0x), _pyr_ptrs(pyr.i0y), _pyr_ptrs(pyr.i1),
+                          _pyr_ptrs(pyr.i1x), _pyr_ptrs(pyr.i1y), pyr.imgpadding, _fp(out), _fp(initflow), pyr.width,
+                          pyr.height, ctypes.byref(cp), prm.nop)
     assert rc == 0
     return out
 
