@@ -51,7 +51,7 @@ typedef struct ofdis_params {
   float dp_thresh, dr_thresh, res_thresh;
   int p_samp_s;            /* patch edge length P (even, P*P*noc % 4 == 0) */
   float patove;            /* patch overlap in [0,1) */
-  int usefbcon;            /* forward-backward merge: must be 0 */
+  int usefbcon;            /* forward-backward merge (oflow.cpp:162-170, patchgrid.cpp:278-375): doubles the patch work */
   int costfct;             /* 0 L2, 1 L1, 2 pseudo-Huber */
   int noc;                 /* image channels: 1 or 3 */
   int patnorm;             /* mean-normalise patches */
@@ -66,7 +66,7 @@ enum {
   OFDIS_OK = 0,
   OFDIS_ERR_ARG = -1,         /* bad argument / unsupported geometry */
   OFDIS_ERR_CUDA = -2,        /* a CUDA call failed; see ofdis_last_error */
-  OFDIS_ERR_UNSUPPORTED = -3, /* valid in the reference but not built here (usefbcon) */
+  OFDIS_ERR_UNSUPPORTED = -3, /* valid in the reference but not built here (levels taller than 1024 rows) */
   OFDIS_ERR_NOMEM = -4
 };
 enum { OFDIS_MEM_HOST = 0, OFDIS_MEM_DEVICE = 1 };
@@ -98,6 +98,12 @@ int ofdis_level_info(const ofdis_ctx* ctx, int level, int* w, int* h, int* nopw,
  * (patch.cpp:90-97) and are not part of this interface. */
 int ofdis_upload_level(ofdis_ctx* ctx, int frame, int level, const float* i0, const float* i0x,
                        const float* i0y, const float* i1, int memkind);
+
+/* Like ofdis_upload_level plus the gradients of the second image (im_bo_dx, im_bo_dy of oflow.h:84-86),
+ * which the forward-backward grid needs as its template gradients (oflow.cpp:193-197).  Required when the
+ * context was created with usefbcon = 1; i1x, i1y may be NULL otherwise. */
+int ofdis_upload_level_fb(ofdis_ctx* ctx, int frame, int level, const float* i0, const float* i0x,
+                          const float* i0y, const float* i1, const float* i1x, const float* i1y, int memkind);
 
 /* Packed transfer: all levels sc_f..sc_l of frames [f0,f1) in the context's own
  * layout (per frame: I0,I1 of levels sc_f..sc_l, then I0x,I0y of the same levels; use

@@ -30,7 +30,7 @@ EXPORTS = [
     "ofdis_debug_varref_iters", "ofdis_launch_count", "ofdis_set_graph_mode", "ofdis_profile_run",
     "ofdis_set_camlr", "ofdis_set_dp_thresh_sq", "ofdis_packed_images_frame_floats", "ofdis_upload_packed_images",
     "ofdis_upload_frames_u8", "ofdis_finest_level_frame_floats", "ofdis_upload_finest_level", "ofdis_get_flow_fullres",
-    "ofdis_get_level",
+    "ofdis_get_level", "ofdis_upload_level_fb",
 ]
 
 
@@ -76,6 +76,7 @@ def lib():
                                              ctypes.c_int, ctypes.c_int]
         L.ofdis_upload_packed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.ofdis_upload_level.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int]
+        L.ofdis_upload_level_fb.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int]
         L.ofdis_level_info.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_IP] * 5
         L.ofdis_patgrid_optimize.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4
         L.ofdis_patgrid_aggregate.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3
@@ -163,9 +164,17 @@ class Context:
     def upload_level(self, frame, level, i0, i0x, i0y, i1, memkind=MEM_HOST):
         self._ck(lib().ofdis_upload_level(self._h, frame, level, _ptr(i0), _ptr(i0x), _ptr(i0y), _ptr(i1), memkind))
 
+    def upload_level_fb(self, frame, level, i0, i0x, i0y, i1, i1x, i1y, memkind=MEM_HOST):
+        """All six arrays of OFClass (oflow.h:84-86); the last two are only used with usefbcon."""
+        self._ck(lib().ofdis_upload_level_fb(self._h, frame, level, _ptr(i0), _ptr(i0x), _ptr(i0y), _ptr(i1), _ptr(i1x),
+                                             _ptr(i1y), memkind))
+
     def upload_pyramids(self, frame: int, pyr):
         for lv in range(self.prm.sc_l, self.prm.sc_f + 1):
-            self.upload_level(frame, lv, pyr.i0[lv], pyr.i0x[lv], pyr.i0y[lv], pyr.i1[lv])
+            if self.prm.usefbcon:
+                self.upload_level_fb(frame, lv, pyr.i0[lv], pyr.i0x[lv], pyr.i0y[lv], pyr.i1[lv], pyr.i1x[lv], pyr.i1y[lv])
+            else:
+                self.upload_level(frame, lv, pyr.i0[lv], pyr.i0x[lv], pyr.i0y[lv], pyr.i1[lv])
 
     @property
     def packed_images_frame_floats(self) -> int:

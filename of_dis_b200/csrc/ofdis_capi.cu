@@ -29,6 +29,10 @@ struct ofdis_ctx {
   bool own_stream = false;
   ofdis_params prm{};
   int nop = 2, width = 0, height = 0, pad = 0, max_frames = 0;
+  // usefbcon: every pair occupies two internal frames (2*f forward, 2*f+1 the grid on the swapped
+  // images); dirs = 2, cap = max_frames * dirs internal frames are allocated
+  int dirs = 1, cap = 0;
+  int last_vr_fstep = 1;
   int nlev = 0;                    // sc_f - sc_l + 1
   std::vector<LevelGeom> lev;      // index: level - sc_l
   std::vector<size_t> img_off;     // [lev][4] offsets (floats) inside one packed frame
@@ -101,11 +105,25 @@ void make_level(LevelGeom& L, const ofdis_ctx* c, int sl) {
   L.ubw = (float)(L.w + p.p_samp_s / 2 - 2);
   L.ubh = (float)(L.h + p.p_samp_s / 2 - 2);
   L.outlierthresh = (float)p.p_samp_s / 2;
+  L.pat_p = L.pat_w = nullptr;
+  L.pat_conv = L.pat_cnt = nullptr;
+  L.fb = 0;
+  L.fstep = 1;
+  L.fb_pos = nullptr;
+  L.fb_wbil = nullptr;
+  L.fb_reach = nullptr;
 }
 
 LevelGeom* level_of(ofdis_ctx* c, int level) {
   if (level < c->prm.sc_l || level > c->prm.sc_f) return nullptr;
   return &c->lev[level - c->prm.sc_l];
+}
+
+// copy of a level's geometry whose launches address every `fstep`-th internal frame
+LevelGeom stepped(const LevelGeom& L, int fstep) {
+  LevelGeom g = L;
+  g.fstep = fstep;
+  return g;
 }
 
 cudaMemcpyKind kind_in(int memkind) { return memkind == OFDIS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
@@ -138,7 +156,6 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
                  int height, int imgpadding, int max_frames) {
   if (!out || !prm) return OFDIS_ERR_ARG;
   *out = nullptr;
-  if (prm->usefbcon) return OFDIS_ERR_UNSUPPORTED;
   if (nop != 1 && nop != 2) return OFDIS_ERR_ARG;
   if (prm->noc != 1 && prm->noc != 3) return OFDIS_ERR_ARG;
   if (prm->sc_l < 0 || prm->sc_f < prm->sc_l || prm->sc_f > 16) return OFDIS_ERR_ARG;
@@ -158,6 +175,9 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
   ctx->height = height;
   ctx->pad = imgpadding;
   ctx->max_frames = max_frames;
+  ctx->dirs = prm->usefbcon ? 2 : 1;
+  ctx->cap = max_frames * ctx->dirs;
+  const int cap = ctx->cap;
   ctx->nlev = prm->sc_f - prm->sc_l + 1;
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) {
@@ -205,21 +225,21 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
   auto dalloc = [&](void** p, size_t bytes) -> bool {
     return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess;
   };
-  bool ok = dalloc((void**)&ctx->d_img, sizeof(float) * ctx->frame_floats * max_frames);
+  bool ok = dalloc((void**)&ctx->d_img, sizeof(float) * ctx->frame_floats * cap);
   ctx->d_flow.assign(ctx->nlev + 1, nullptr);
   ctx->flow_floats.assign(ctx->nlev + 1, 0);
   for (int li = 0; li <= ctx->nlev && ok; ++li) {
     const int sl = prm->sc_l + li;
     const size_t n = (size_t)(width >> sl) * (height >> sl) * nop;
     ctx->flow_floats[li] = n;
-    ok = dalloc((void**)&ctx->d_flow[li], sizeof(float) * n * max_frames);
-    if (ok) cudaMemsetAsync(ctx->d_flow[li], 0, sizeof(float) * n * max_frames, ctx->stream);
+    ok = dalloc((void**)&ctx->d_flow[li], sizeof(float) * n * cap);
+    if (ok) cudaMemsetAsync(ctx->d_flow[li], 0, sizeof(float) * n * cap, ctx->stream);
   }
   for (int li = 0; li < ctx->nlev && ok; ++li) {
     LevelGeom& L = ctx->lev[li];
     // device: block A = [frame][I0,I1 of all levels], block B = [frame][I0x,I0y of all levels]
     const size_t gfl = ctx->frame_floats - ctx->images_floats;
-    float* blockB = ctx->d_img + ctx->images_floats * max_frames;
+    float* blockB = ctx->d_img + ctx->images_floats * cap;
     for (int k = 0; k < 4; ++k) {
       const size_t o = ctx->img_off[(size_t)li * 4 + k];
       const bool is_img = (k == 0 || k == 3);
@@ -230,10 +250,20 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
     L.flow_frame_stride = ctx->flow_floats[li];
     L.flow_prev = ctx->d_flow[li + 1];
     L.flow_prev_frame_stride = ctx->flow_floats[li + 1];
-    ok = ok && dalloc((void**)&L.pat_p, sizeof(float) * L.np * nop * max_frames);
-    ok = ok && dalloc((void**)&L.pat_w, sizeof(float) * (size_t)L.np * L.novals * max_frames);
-    ok = ok && dalloc((void**)&L.pat_conv, sizeof(int) * L.np * max_frames);
-    ok = ok && dalloc((void**)&L.pat_cnt, sizeof(int) * L.np * max_frames);
+    ok = ok && dalloc((void**)&L.pat_p, sizeof(float) * L.np * nop * cap);
+    ok = ok && dalloc((void**)&L.pat_w, sizeof(float) * (size_t)L.np * L.novals * cap);
+    ok = ok && dalloc((void**)&L.pat_conv, sizeof(int) * L.np * cap);
+    ok = ok && dalloc((void**)&L.pat_cnt, sizeof(int) * L.np * cap);
+    L.fb = ctx->dirs == 2 ? 1 : 0;
+    L.fstep = 1;
+    L.fb_pos = nullptr;
+    L.fb_wbil = nullptr;
+    L.fb_reach = nullptr;
+    if (L.fb) {
+      ok = ok && dalloc((void**)&L.fb_pos, sizeof(int) * 2 * L.np * cap);
+      ok = ok && dalloc((void**)&L.fb_wbil, sizeof(float) * 4 * L.np * cap);
+      ok = ok && dalloc((void**)&L.fb_reach, sizeof(int) * cap);
+    }
   }
   if (ok && prm->usetvref) {
     // refinement planes sized for the finest level: mask, avg[C], 8 x deriv[C], dudv (2), rec (8)
@@ -243,15 +273,15 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
     // skewed SOR arrays: (W4 + h) diagonals x hpad rows, 8 (rec) + 2 (dudv) float4 per block
     const size_t diag = (size_t)((Lf.w + 3) / 4 + Lf.h + 2) * sor_hpad(Lf.h);
     const size_t per_frame = plane * (1 + C + 8 * C) + diag * 4 * (8 + 2);
-    ok = dalloc((void**)&ctx->d_planes, sizeof(float) * per_frame * max_frames);
+    ok = dalloc((void**)&ctx->d_planes, sizeof(float) * per_frame * cap);
     if (ok) {
       float* q = ctx->d_planes;
       VarRefPlanes& P = ctx->planes;
-      P.rec = reinterpret_cast<float4*>(q); q += diag * 4 * 8 * max_frames;   // records first (alignment)
-      P.dudv = reinterpret_cast<float4*>(q); q += diag * 4 * 2 * max_frames;
-      P.mask = q; q += plane * max_frames;
-      P.avg = q; q += plane * C * max_frames;
-      for (int k = 0; k < 8; ++k) { P.deriv[k] = q; q += plane * C * max_frames; }
+      P.rec = reinterpret_cast<float4*>(q); q += diag * 4 * 8 * cap;   // records first (alignment)
+      P.dudv = reinterpret_cast<float4*>(q); q += diag * 4 * 2 * cap;
+      P.mask = q; q += plane * cap;
+      P.avg = q; q += plane * C * cap;
+      for (int k = 0; k < 8; ++k) { P.deriv[k] = q; q += plane * C * cap; }
       P.plane = plane;
     }
   }
@@ -277,6 +307,9 @@ int ofdis_destroy(ofdis_ctx* ctx) {
     cudaFree(L.pat_w);
     cudaFree(L.pat_conv);
     cudaFree(L.pat_cnt);
+    cudaFree(L.fb_pos);
+    cudaFree(L.fb_wbil);
+    cudaFree(L.fb_reach);
   }
   cudaFree(ctx->d_planes);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -318,11 +351,29 @@ int ofdis_upload_level(ofdis_ctx* ctx, int frame, int level, const float* i0, co
   LevelGeom* L = level_of(ctx, level);
   if (!L || frame < 0 || frame >= ctx->max_frames || !i0 || !i0x || !i0y || !i1) return fail(ctx, OFDIS_ERR_ARG, "upload_level: bad argument");
   CK(cudaSetDevice(ctx->device));
+  if (ctx->dirs == 2) return fail(ctx, OFDIS_ERR_ARG, "upload_level: usefbcon needs the gradients of the second image, use ofdis_upload_level_fb");
   const size_t n = (size_t)L->tmp_w * L->tmp_h * L->noc;
   const float* src[4] = {i0, i0x, i0y, i1};
   for (int k = 0; k < 4; ++k)
     CK(cudaMemcpyAsync(const_cast<float*>(L->img[k]) + (size_t)frame * L->img_fs[k], src[k], sizeof(float) * n,
                        kind_in(memkind), ctx->stream));
+  return OFDIS_OK;
+}
+
+int ofdis_upload_level_fb(ofdis_ctx* ctx, int frame, int level, const float* i0, const float* i0x, const float* i0y,
+                          const float* i1, const float* i1x, const float* i1y, int memkind) {
+  if (!ctx) return OFDIS_ERR_ARG;
+  LevelGeom* L = level_of(ctx, level);
+  if (!L || frame < 0 || frame >= ctx->max_frames || !i0 || !i0x || !i0y || !i1) return fail(ctx, OFDIS_ERR_ARG, "upload_level_fb: bad argument");
+  if (ctx->dirs == 2 && (!i1x || !i1y)) return fail(ctx, OFDIS_ERR_ARG, "upload_level_fb: usefbcon needs i1x, i1y");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)L->tmp_w * L->tmp_h * L->noc;
+  // forward frame: template I0 (+ gradients), target I1; backward frame: the swapped pair (oflow.cpp:191-197)
+  const float* src[2][4] = {{i0, i0x, i0y, i1}, {i1, i1x, i1y, i0}};
+  for (int d = 0; d < ctx->dirs; ++d)
+    for (int k = 0; k < 4; ++k)
+      CK(cudaMemcpyAsync(const_cast<float*>(L->img[k]) + (size_t)(frame * ctx->dirs + d) * L->img_fs[k], src[d][k],
+                         sizeof(float) * n, kind_in(memkind), ctx->stream));
   return OFDIS_OK;
 }
 
@@ -332,7 +383,7 @@ int ofdis_get_level(ofdis_ctx* ctx, int frame, int level, int which, float* dst,
   if (!L || frame < 0 || frame >= ctx->max_frames || which < 0 || which > 3 || !dst) return fail(ctx, OFDIS_ERR_ARG, "get_level: bad argument");
   CK(cudaSetDevice(ctx->device));
   const size_t n = (size_t)L->tmp_w * L->tmp_h * L->noc;
-  CK(cudaMemcpyAsync(dst, L->img[which] + (size_t)frame * L->img_fs[which], sizeof(float) * n, kind_out(memkind), ctx->stream));
+  CK(cudaMemcpyAsync(dst, L->img[which] + (size_t)frame * ctx->dirs * L->img_fs[which], sizeof(float) * n, kind_out(memkind), ctx->stream));
   if (memkind != OFDIS_MEM_DEVICE) CK(cudaStreamSynchronize(ctx->stream));
   return OFDIS_OK;
 }
@@ -347,6 +398,7 @@ size_t ofdis_packed_offset(const ofdis_ctx* ctx, int level, int which) {
 int ofdis_upload_packed(ofdis_ctx* ctx, int f0, int f1, const float* packed, int memkind) {
   if (!ctx) return OFDIS_ERR_ARG;
   if (f0 < 0 || f1 > ctx->max_frames || f0 >= f1 || !packed) return fail(ctx, OFDIS_ERR_ARG, "upload_packed: bad argument");
+  if (ctx->dirs == 2) return fail(ctx, OFDIS_ERR_UNSUPPORTED, "upload_packed: a packed frame has no gradients of the second image; with usefbcon use ofdis_upload_level_fb or one of the image-only uploads");
   CK(cudaSetDevice(ctx->device));
   // host: [frame][images | gradients]; device: all images, then all gradients -> two 2-D copies
   const size_t nif = ctx->images_floats, ngf = ctx->frame_floats - nif;
@@ -358,36 +410,50 @@ int ofdis_upload_packed(ofdis_ctx* ctx, int f0, int f1, const float* packed, int
   return OFDIS_OK;
 }
 
+// Images of the forward frames are in place: fill the backward frames with the swapped pair
+// (usefbcon) and derive the template gradients of every internal frame on every level.
+static int finish_gradients(ofdis_ctx* ctx, int f0, int f1) {
+  const int D = ctx->dirs, q0 = f0 * D, q1 = f1 * D;
+  for (int sl = ctx->prm.sc_f; sl >= ctx->prm.sc_l; --sl) {
+    const LevelGeom& L = ctx->lev[sl - ctx->prm.sc_l];
+    if (D == 2) {
+      if (launch_swap_images(L, q0, q1, ctx->stream) < 0) return fail(ctx, OFDIS_ERR_CUDA, "swap_images_kernel launch", cudaGetLastError());
+      ctx->launches += 1;
+    }
+    if (launch_sobel(L, q0, q1, ctx->stream) < 0) return fail(ctx, OFDIS_ERR_CUDA, "sobel_kernel launch", cudaGetLastError());
+    ctx->launches += 1;
+  }
+  return OFDIS_OK;
+}
+
 size_t ofdis_packed_images_frame_floats(const ofdis_ctx* ctx) { return ctx ? ctx->images_floats : 0; }
 
 int ofdis_upload_packed_images(ofdis_ctx* ctx, int f0, int f1, const float* packed, int memkind) {
   if (!ctx) return OFDIS_ERR_ARG;
   if (f0 < 0 || f1 > ctx->max_frames || f0 >= f1 || !packed) return fail(ctx, OFDIS_ERR_ARG, "upload_packed_images: bad argument");
   CK(cudaSetDevice(ctx->device));
-  // images of consecutive frames are contiguous on the device: one plain copy
-  CK(cudaMemcpyAsync(ctx->d_img + (size_t)f0 * ctx->images_floats, packed,
-                     sizeof(float) * ctx->images_floats * (f1 - f0), kind_in(memkind), ctx->stream));
-  for (int sl = ctx->prm.sc_f; sl >= ctx->prm.sc_l; --sl) {
-    const int n = launch_sobel(ctx->lev[sl - ctx->prm.sc_l], f0, f1, ctx->stream);
-    if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "sobel_kernel launch", cudaGetLastError());
-    ctx->launches += n;
-  }
-  return OFDIS_OK;
+  // images of consecutive internal frames are contiguous on the device: one copy (strided over the
+  // forward frames when every pair also has a backward frame)
+  const int D = ctx->dirs;
+  const size_t nif = ctx->images_floats;
+  if (D == 1)
+    CK(cudaMemcpyAsync(ctx->d_img + (size_t)f0 * nif, packed, sizeof(float) * nif * (f1 - f0), kind_in(memkind), ctx->stream));
+  else
+    CK(cudaMemcpy2DAsync(ctx->d_img + (size_t)f0 * D * nif, sizeof(float) * nif * D, packed, sizeof(float) * nif,
+                         sizeof(float) * nif, (size_t)(f1 - f0), kind_in(memkind), ctx->stream));
+  return finish_gradients(ctx, f0, f1);
 }
 
-// Coarser levels by 2x2 box means, then the gradients of I0 on every level.
+// Coarser levels by 2x2 box means (forward frames), then finish_gradients.
 static int finish_pyramid(ofdis_ctx* ctx, int f0, int f1) {
-  for (int sl = ctx->prm.sc_l; sl <= ctx->prm.sc_f; ++sl) {
-    LevelGeom& L = ctx->lev[sl - ctx->prm.sc_l];
-    if (sl > ctx->prm.sc_l) {
-      if (launch_pyr_down(ctx->lev[sl - 1 - ctx->prm.sc_l], L, f0, f1, ctx->stream) < 0)
-        return fail(ctx, OFDIS_ERR_CUDA, "pyr_down_kernel launch", cudaGetLastError());
-      ctx->launches += 1;
-    }
-    if (launch_sobel(L, f0, f1, ctx->stream) < 0) return fail(ctx, OFDIS_ERR_CUDA, "sobel_kernel launch", cudaGetLastError());
+  const int D = ctx->dirs, q0 = f0 * D, nq = f1 - f0;
+  for (int sl = ctx->prm.sc_l + 1; sl <= ctx->prm.sc_f; ++sl) {
+    const LevelGeom gs = stepped(ctx->lev[sl - 1 - ctx->prm.sc_l], D), gd = stepped(ctx->lev[sl - ctx->prm.sc_l], D);
+    if (launch_pyr_down(gs, gd, q0, q0 + nq, ctx->stream) < 0)
+      return fail(ctx, OFDIS_ERR_CUDA, "pyr_down_kernel launch", cudaGetLastError());
     ctx->launches += 1;
   }
-  return OFDIS_OK;
+  return finish_gradients(ctx, f0, f1);
 }
 
 static int ensure_stage(ofdis_ctx* ctx, size_t bytes) {
@@ -432,7 +498,7 @@ int ofdis_upload_frames_u8(ofdis_ctx* ctx, int f0, int f1, const unsigned char* 
     CK(cudaMemcpyAsync(ctx->d_stage, frames, bytes, cudaMemcpyHostToDevice, ctx->stream));
     src.frames = static_cast<const unsigned char*>(ctx->d_stage);
   }
-  if (launch_pyr_from_u8(ctx->lev[0], f0, f1, src, ctx->stream) < 0)
+  if (launch_pyr_from_u8(stepped(ctx->lev[0], ctx->dirs), f0 * ctx->dirs, f0 * ctx->dirs + (f1 - f0), src, ctx->stream) < 0)
     return fail(ctx, OFDIS_ERR_CUDA, "pyr_from_u8_kernel launch", cudaGetLastError());
   ctx->launches += 1;
   return finish_pyramid(ctx, f0, f1);
@@ -454,7 +520,7 @@ int ofdis_upload_finest_level(ofdis_ctx* ctx, int f0, int f1, const float* packe
     CK(cudaMemcpyAsync(ctx->d_stage, packed, sizeof(float) * per * (size_t)(f1 - f0), cudaMemcpyHostToDevice, ctx->stream));
     src = static_cast<const float*>(ctx->d_stage);
   }
-  if (launch_pyr_from_level(ctx->lev[0], f0, f1, src, ctx->stream) < 0)
+  if (launch_pyr_from_level(stepped(ctx->lev[0], ctx->dirs), f0 * ctx->dirs, f0 * ctx->dirs + (f1 - f0), src, ctx->stream) < 0)
     return fail(ctx, OFDIS_ERR_CUDA, "pyr_from_level_kernel launch", cudaGetLastError());
   ctx->launches += 1;
   return finish_pyramid(ctx, f0, f1);
@@ -482,7 +548,8 @@ int ofdis_get_flow_fullres(ofdis_ctx* ctx, int f0, int f1, float* out, int width
     }
     dst = ctx->d_full;
   }
-  if (launch_flow_upsample(ctx->lev[0], f0, f1, dst, width_org, height_org, cx, cy, ctx->stream) < 0)
+  if (launch_flow_upsample(stepped(ctx->lev[0], ctx->dirs), f0 * ctx->dirs, f0 * ctx->dirs + (f1 - f0), dst, width_org, height_org,
+                           cx, cy, ctx->stream) < 0)
     return fail(ctx, OFDIS_ERR_CUDA, "flow_upsample_kernel launch", cudaGetLastError());
   ctx->launches += 1;
   if (memkind != OFDIS_MEM_DEVICE)
@@ -494,7 +561,7 @@ int ofdis_patgrid_optimize(ofdis_ctx* ctx, int level, int f0, int f1, int init_f
   if (!ctx) return OFDIS_ERR_ARG;
   LevelGeom* L = level_of(ctx, level);
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_optimize: bad argument");
-  const int n = launch_patch_optimize(*L, ctx->pp, f0, f1, init_from_coarser != 0, ctx->stream, ctx->prof);
+  const int n = launch_patch_optimize(*L, ctx->pp, f0 * ctx->dirs, f1 * ctx->dirs, init_from_coarser != 0, ctx->stream, ctx->prof);
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "patch_optimize_kernel launch", cudaGetLastError());
   ctx->launches += n;
   return OFDIS_OK;
@@ -504,7 +571,16 @@ int ofdis_patgrid_aggregate(ofdis_ctx* ctx, int level, int f0, int f1) {
   if (!ctx) return OFDIS_ERR_ARG;
   LevelGeom* L = level_of(ctx, level);
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_aggregate: bad argument");
-  const int n = launch_densify(*L, f0, f1, ctx->stream, ctx->prof);
+  int n;
+  if (ctx->dirs == 2) {
+    // both grids' patch positions first; the backward flow is not densified on the last level (oflow.cpp:269-270)
+    if (launch_fb_prepare(*L, f0 * 2, f1 * 2, ctx->stream) < 0) return fail(ctx, OFDIS_ERR_CUDA, "fb_prepare_kernel launch", cudaGetLastError());
+    ctx->launches += 1;
+    n = (level == ctx->prm.sc_l) ? launch_densify(stepped(*L, 2), f0 * 2, f0 * 2 + (f1 - f0), ctx->stream, ctx->prof)
+                                 : launch_densify(*L, f0 * 2, f1 * 2, ctx->stream, ctx->prof);
+  } else {
+    n = launch_densify(*L, f0, f1, ctx->stream, ctx->prof);
+  }
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "densify_kernel launch", cudaGetLastError());
   ctx->launches += n;
   return OFDIS_OK;
@@ -531,11 +607,16 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
     pl.rec_stride = diag * (L->nop == 2 ? 8 : 5);
     pl.dudv_stride = diag * 2;
   }
-  const int n = launch_varref(*L, pl, vp, f0, f1, ctx->stream, ctx->prof);
+  // usefbcon: both directions are refined except on the last level (oflow.cpp:285-294)
+  const int D = ctx->dirs;
+  const bool fwd_only = (D == 2 && level == ctx->prm.sc_l);
+  const int n = fwd_only ? launch_varref(stepped(*L, 2), pl, vp, f0 * 2, f0 * 2 + (f1 - f0), ctx->stream, ctx->prof)
+                         : launch_varref(*L, pl, vp, f0 * D, f1 * D, ctx->stream, ctx->prof);
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "varref kernels launch", cudaGetLastError());
   ctx->launches += n;
   ctx->last_vr_level = level;
   ctx->last_vr_f0 = f0;
+  ctx->last_vr_fstep = fwd_only ? 1 : D;  // workspace slots per user frame
   return OFDIS_OK;
 }
 
@@ -594,7 +675,7 @@ int ofdis_get_flow(ofdis_ctx* ctx, int frame, int level, float* dst, int memkind
   if (!ctx) return OFDIS_ERR_ARG;
   const int li = flow_index(ctx, level);
   if (li < 0 || frame < 0 || frame >= ctx->max_frames || !dst) return fail(ctx, OFDIS_ERR_ARG, "get_flow: bad argument");
-  CK(cudaMemcpyAsync(dst, ctx->d_flow[li] + (size_t)frame * ctx->flow_floats[li], sizeof(float) * ctx->flow_floats[li],
+  CK(cudaMemcpyAsync(dst, ctx->d_flow[li] + (size_t)frame * ctx->dirs * ctx->flow_floats[li], sizeof(float) * ctx->flow_floats[li],
                      kind_out(memkind), ctx->stream));
   if (memkind == OFDIS_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
   return OFDIS_OK;
@@ -604,7 +685,7 @@ int ofdis_set_flow(ofdis_ctx* ctx, int frame, int level, const float* src, int m
   if (!ctx) return OFDIS_ERR_ARG;
   const int li = flow_index(ctx, level);
   if (li < 0 || frame < 0 || frame >= ctx->max_frames || !src) return fail(ctx, OFDIS_ERR_ARG, "set_flow: bad argument");
-  CK(cudaMemcpyAsync(ctx->d_flow[li] + (size_t)frame * ctx->flow_floats[li], src, sizeof(float) * ctx->flow_floats[li],
+  CK(cudaMemcpyAsync(ctx->d_flow[li] + (size_t)frame * ctx->dirs * ctx->flow_floats[li], src, sizeof(float) * ctx->flow_floats[li],
                      kind_in(memkind), ctx->stream));
   return OFDIS_OK;
 }
@@ -612,8 +693,12 @@ int ofdis_set_flow(ofdis_ctx* ctx, int frame, int level, const float* src, int m
 int ofdis_get_flow_batch(ofdis_ctx* ctx, int f0, int f1, float* dst, int memkind) {
   if (!ctx) return OFDIS_ERR_ARG;
   if (f0 < 0 || f1 > ctx->max_frames || f0 >= f1 || !dst) return fail(ctx, OFDIS_ERR_ARG, "get_flow_batch: bad argument");
-  CK(cudaMemcpyAsync(dst, ctx->d_flow[0] + (size_t)f0 * ctx->flow_floats[0], sizeof(float) * ctx->flow_floats[0] * (f1 - f0),
-                     kind_out(memkind), ctx->stream));
+  const size_t nfl = ctx->flow_floats[0];
+  if (ctx->dirs == 1)
+    CK(cudaMemcpyAsync(dst, ctx->d_flow[0] + (size_t)f0 * nfl, sizeof(float) * nfl * (f1 - f0), kind_out(memkind), ctx->stream));
+  else  // forward frames only
+    CK(cudaMemcpy2DAsync(dst, sizeof(float) * nfl, ctx->d_flow[0] + (size_t)f0 * 2 * nfl, sizeof(float) * nfl * 2,
+                         sizeof(float) * nfl, (size_t)(f1 - f0), kind_out(memkind), ctx->stream));
   return OFDIS_OK;
 }
 
@@ -622,6 +707,7 @@ int ofdis_get_patches(ofdis_ctx* ctx, int frame, int level, float* p, float* pwe
   LevelGeom* L = level_of(ctx, level);
   if (!L || frame < 0 || frame >= ctx->max_frames) return fail(ctx, OFDIS_ERR_ARG, "get_patches: bad argument");
   const size_t np = L->np;
+  frame *= ctx->dirs;  // the forward grid
   if (p) CK(cudaMemcpyAsync(p, L->pat_p + frame * np * L->nop, sizeof(float) * np * L->nop, cudaMemcpyDeviceToHost, ctx->stream));
   if (pweight) CK(cudaMemcpyAsync(pweight, L->pat_w + frame * np * L->novals, sizeof(float) * np * L->novals, cudaMemcpyDeviceToHost, ctx->stream));
   if (conv) CK(cudaMemcpyAsync(conv, L->pat_conv + frame * np, sizeof(int) * np, cudaMemcpyDeviceToHost, ctx->stream));
@@ -633,7 +719,7 @@ int ofdis_get_patches(ofdis_ctx* ctx, int frame, int level, float* p, float* pwe
 long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, size_t max_floats) {
   if (!ctx || !name || !dst || ctx->last_vr_level < 0) return OFDIS_ERR_ARG;
   LevelGeom* L = level_of(ctx, ctx->last_vr_level);
-  const int fr = frame - ctx->last_vr_f0;
+  const int fr = (frame - ctx->last_vr_f0) * ctx->last_vr_fstep;
   if (!L || fr < 0) return OFDIS_ERR_ARG;
   const size_t plane = (size_t)L->pitch * L->h;
   const int C = L->noc;

@@ -27,7 +27,17 @@ struct LevelGeom {
   float* pat_w;            // [frames][np][novals]
   int* pat_conv;           // [frames][np]
   int* pat_cnt;            // [frames][np]
+  // Forward-backward consistency (usefbcon, oflow.cpp:162-170): internal frame q = 2*pair + dir,
+  // dir 1 = the grid on the swapped images; the complementary frame of q is q ^ 1.
+  int fb;                  // 1: frames come in (forward, backward) couples; stereo camlr = q & 1
+  int fstep;               // frame step of a launch: frame = f0 + index * fstep (2 = forward frames only)
+  int* fb_pos;             // [frames][np][2]  integer patch position after optimisation (patchgrid.cpp:308-309)
+  float* fb_wbil;          // [frames][np][4]  bilinear weights of that position (:313-318)
+  int* fb_reach;           // [frames]         max |position - reference| over the frame's patches
 };
+
+__host__ __device__ __forceinline__ int frame_of(const LevelGeom& g, int f0, int idx) { return f0 + idx * g.fstep; }
+__host__ __device__ __forceinline__ int camlr_of(const LevelGeom& g, int frame) { return g.fb ? (frame & 1) : g.camlr; }
 
 struct PatchParams {
   int max_iter, min_iter, costfct, patnorm;
@@ -91,6 +101,9 @@ struct ProfScope {
 int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int f1, bool init_from_coarser,
                           cudaStream_t st, Profiler* prof = nullptr);
 int launch_densify(const LevelGeom& g, int f0, int f1, cudaStream_t st, Profiler* prof = nullptr);
+// usefbcon: positions/weights of every patch (all frames of [f0,f1)), then the merged gather
+int launch_fb_prepare(const LevelGeom& g, int f0, int f1, cudaStream_t st);
+int launch_swap_images(const LevelGeom& g, int f0, int f1, cudaStream_t st);
 // pyramid_kernels.cu -- callers either side of the hot path
 struct PyrSourceU8 {
   const unsigned char* frames;  // [frame][2][h_org][w_org][noc], device

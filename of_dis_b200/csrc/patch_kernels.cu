@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) patch_optimize_kernel(LevelGeom g, PatchP
           } else {
             dp0 = (b0 / L00) / L00;
             p0 = p0 - dp0;
-            p0 = (g.camlr == 0) ? std_min(p0, 0.0f) : std_max(p0, 0.0f);
+            p0 = (camlr_of(g, frame) == 0) ? std_min(p0, 0.0f) : std_max(p0, 0.0f);
             ptx = refx + p0;
           }
           const float ex = stx - ptx, ey = sty - pty;
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256) patch_p8c1_kernel(LevelGeom g, PatchParam
           } else {
             dp0 = (b0 / L00) / L00;
             p0 = p0 - dp0;
-            p0 = (g.camlr == 0) ? std_min(p0, 0.0f) : std_max(p0, 0.0f);
+            p0 = (camlr_of(g, frame) == 0) ? std_min(p0, 0.0f) : std_max(p0, 0.0f);
             ptx = refx + p0;
           }
           const float ex = stx - ptx, ey = sty - pty;
@@ -508,6 +508,65 @@ __global__ void __launch_bounds__(256) patch_p8c1_kernel(LevelGeom g, PatchParam
   }
 }
 
+// usefbcon, second loop of AggregateFlowDense (patchgrid.cpp:278-375) as a gather: the patches of
+// the complementary frame `cq`, at their displaced positions, add their NEGATED flow with bilinear
+// weights.  The reference's scatter visits patches in ascending ip and the pixels of a patch in
+// raster order, so this cell receives at most four terms per patch -- from the patch pixels at
+// (xi,yi) [wbil0], (xi+1,yi) [wbil1], (xi,yi+1) [wbil2], (xi+1,yi+1) [wbil3], in that order.  Only
+// patches whose reference lies within `reach` (+ patch extent) of the cell can contribute.
+template <int NOP>
+__device__ __forceinline__ void densify_merge_complement(const LevelGeom& g, int cq, int xi, int yi, float& we,
+                                                         float& a0, float& a1) {
+  const int P = g.P, C = g.noc, n = g.novals, lb = -P / 2, ub = P / 2 - 1;
+  const float* pp = g.pat_p + (size_t)cq * g.np * NOP;
+  const float* pw = g.pat_w + (size_t)cq * g.np * n;
+  const int* pos = g.fb_pos + (size_t)cq * g.np * 2;
+  const float* wb = g.fb_wbil + (size_t)cq * g.np * 4;
+  const int reach = g.fb_reach[cq];
+  // a patch at position pos covers cells pos+lb-1 .. pos+ub; |pos - ref| <= reach
+  int gx0 = xi - ub - reach - g.offw, gx1 = xi - lb + 1 + reach - g.offw;
+  gx0 = gx0 <= 0 ? 0 : (gx0 + g.steps - 1) / g.steps;
+  gx1 = gx1 < 0 ? -1 : gx1 / g.steps;
+  if (gx1 > g.nopw - 1) gx1 = g.nopw - 1;
+  int gy0 = yi - ub - reach - g.offh, gy1 = yi - lb + 1 + reach - g.offh;
+  gy0 = gy0 <= 0 ? 0 : (gy0 + g.steps - 1) / g.steps;
+  gy1 = gy1 < 0 ? -1 : gy1 / g.steps;
+  if (gy1 > g.noph - 1) gy1 = g.noph - 1;
+  for (int gx = gx0; gx <= gx1; ++gx)
+    for (int gy = gy0; gy <= gy1; ++gy) {
+      const int ip = gx * g.noph + gy;
+      const int p0 = pos[2 * ip], p1 = pos[2 * ip + 1];
+      if (xi < p0 + lb - 1 || xi > p0 + ub || yi < p1 + lb - 1 || yi > p1 + ub) continue;
+      // in-image rectangle of this patch (the reference tests xt>=1, yt>=1, xt<w-1, yt<h-1), patch coordinates
+      int x0 = 1 - p0 - lb, x1 = g.w - 2 - p0 - lb, y0 = 1 - p1 - lb;
+      x0 = x0 < 0 ? 0 : x0;
+      x1 = x1 > P - 1 ? P - 1 : x1;
+      y0 = y0 < 0 ? 0 : y0;
+      const float f0v = pp[ip * NOP], f1v = (NOP == 2) ? pp[ip * NOP + 1] : 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int xt = xi + (t & 1), yt = yi + (t >> 1);
+        const int rx = xt - p0 - lb, ry = yt - p1 - lb;
+        if (rx < 0 || rx > P - 1 || ry < 0 || ry > P - 1) continue;
+        if (!(xt >= 1 && yt >= 1 && xt < g.w - 1 && yt < g.h - 1)) continue;
+        // weight cursor: +1 per pixel and +(C-1) per in-image pixel before this one (patchgrid.cpp:331-339)
+        const float* q = pw + (size_t)ip * n + (ry * P + rx) + (C - 1) * ((ry - y0) * (x1 - x0 + 1) + (rx - x0));
+        float absw;
+        if (C == 1) {
+          absw = 1.0f / std_max(2.0f, q[0]);
+        } else {
+          absw = std_max(2.0f, q[0]);
+          for (int c = 1; c < C; ++c) absw += std_max(2.0f, q[c]);
+          absw = 1.0f / absw;
+        }
+        const float wt = wb[4 * ip + t];
+        we += wt * absw;
+        a0 -= wt * (f0v * absw);
+        if (NOP == 2) a1 -= wt * (f1v * absw);
+      }
+    }
+}
+
 // K4: PatGridClass::AggregateFlowDense (patchgrid.cpp:213-275,377-394) as a
 // per-pixel gather.  The reference scatters patch by patch in ip = x*noph + y
 // order; visiting the covering patches of a pixel in ascending (x, y) grid order
@@ -516,7 +575,7 @@ template <int NOP>
 __global__ void __launch_bounds__(256) densify_kernel(LevelGeom g, int f0) {
   const int xi = blockIdx.x * blockDim.x + threadIdx.x;
   const int yi = blockIdx.y * blockDim.y + threadIdx.y;
-  const int frame = f0 + blockIdx.z;
+  const int frame = frame_of(g, f0, blockIdx.z);
   if (xi >= g.w || yi >= g.h) return;
   const int P = g.P, C = g.noc, n = g.novals, hp = P / 2;
   const float* pp = g.pat_p + (size_t)frame * g.np * NOP;
@@ -558,6 +617,7 @@ __global__ void __launch_bounds__(256) densify_kernel(LevelGeom g, int f0) {
       if (NOP == 2) a1 += pp[ip * NOP + 1] * absw;
     }
   }
+  if (g.fb) densify_merge_complement<NOP>(g, frame ^ 1, xi, yi, we, a0, a1);
   float* out = g.flow + (size_t)frame * g.flow_frame_stride + ((size_t)yi * g.w + xi) * NOP;
   if (we > 0.f) {
     a0 = a0 / we;
@@ -565,6 +625,57 @@ __global__ void __launch_bounds__(256) densify_kernel(LevelGeom g, int f0) {
   }
   out[0] = a0;
   if (NOP == 2) out[1] = a1;
+}
+
+// Swapped copy of the image pair into the backward frame of every couple: its template is I1,
+// its target I0 (oflow.cpp:193-197).  Gradients are derived afterwards by sobel_kernel.
+__global__ void __launch_bounds__(256) swap_images_kernel(LevelGeom g, int f0) {
+  const size_t n = (size_t)g.tmp_w * g.tmp_h * g.noc;
+  const int fwd = f0 + 2 * blockIdx.y, bwd = fwd + 1;
+  const float* a = g.img[0] + (size_t)fwd * g.img_fs[0];
+  const float* b = g.img[3] + (size_t)fwd * g.img_fs[3];
+  float* a2 = const_cast<float*>(g.img[0]) + (size_t)bwd * g.img_fs[0];
+  float* b2 = const_cast<float*>(g.img[3]) + (size_t)bwd * g.img_fs[3];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    a2[i] = b[i];
+    b2[i] = a[i];
+  }
+}
+
+// usefbcon, first half of the second loop of AggregateFlowDense (patchgrid.cpp:296-318): per patch the
+// integer position after optimisation and its bilinear weights; per frame how far any patch moved
+// (bounds the gather window of densify_merge_complement exactly).  One CTA per frame.
+template <int NOP>
+__global__ void __launch_bounds__(256) fb_prepare_kernel(LevelGeom g, int f0) {
+  __shared__ int s_max[256];
+  const int frame = f0 + blockIdx.x;
+  const float* pp = g.pat_p + (size_t)frame * g.np * NOP;
+  int* pos = g.fb_pos + (size_t)frame * g.np * 2;
+  float* wb = g.fb_wbil + (size_t)frame * g.np * 4;
+  int reach = 0;
+  for (int ip = threadIdx.x; ip < g.np; ip += blockDim.x) {
+    const int gx = ip / g.noph, gy = ip - gx * g.noph;
+    const int cx = gx * g.steps + g.offw, cy = gy * g.steps + g.offh;
+    // GetPointPos() == pt_ref + p_iter (patch.cpp:214-221; stereo keeps the row)
+    const float rpx = (float)cx + pp[ip * NOP], rpy = (NOP == 2) ? (float)cy + pp[ip * NOP + 1] : (float)cy;
+    const int p0 = (int)ceil((double)rpx + .00001), p1 = (int)ceil((double)rpy + .00001);  // double literal in the reference
+    const float r0 = rpx - (float)(int)floorf(rpx), r1 = rpy - (float)(int)floorf(rpy);
+    pos[2 * ip] = p0;
+    pos[2 * ip + 1] = p1;
+    wb[4 * ip] = r0 * r1;
+    wb[4 * ip + 1] = (1.f - r0) * r1;
+    wb[4 * ip + 2] = r0 * (1.f - r1);
+    wb[4 * ip + 3] = (1.f - r0) * (1.f - r1);
+    const int dx = p0 > cx ? p0 - cx : cx - p0, dy = p1 > cy ? p1 - cy : cy - p1;
+    reach = max(reach, max(dx, dy));
+  }
+  s_max[threadIdx.x] = reach;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_max[threadIdx.x] = max(s_max[threadIdx.x], s_max[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) g.fb_reach[frame] = s_max[0];
 }
 
 
@@ -597,6 +708,20 @@ int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+int launch_fb_prepare(const LevelGeom& g, int f0, int f1, cudaStream_t st) {
+  if (g.nop == 2) fb_prepare_kernel<2><<<f1 - f0, 256, 0, st>>>(g, f0);
+  else fb_prepare_kernel<1><<<f1 - f0, 256, 0, st>>>(g, f0);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_swap_images(const LevelGeom& g, int f0, int f1, cudaStream_t st) {  // [f0,f1): internal frames, couples
+  const size_t n = (size_t)g.tmp_w * g.tmp_h * g.noc;
+  const dim3 grid((unsigned)((n + 1023) / 1024 > 64 ? 64 : (n + 1023) / 1024), (f1 - f0) / 2);
+  swap_images_kernel<<<grid, 256, 0, st>>>(g, f0);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// [f0,f1) are launch indices: frame = f0 + index * g.fstep
 int launch_densify(const LevelGeom& g, int f0, int f1, cudaStream_t st, Profiler* prof) {
   ProfScope scope(prof, KC_DENSIFY);
   const dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8, f1 - f0);

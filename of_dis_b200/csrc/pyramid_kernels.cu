@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) pyr_from_u8_kernel(LevelGeom g, int f0, P
   const int C = g.noc, sh = g.level, n = 1 << sh;
   const unsigned char* src = s.frames + ((size_t)fr * 2 + k) * s.image_bytes;
   const int arr = k ? 3 : 0;
-  float* dst = const_cast<float*>(g.img[arr]) + (size_t)(f0 + fr) * g.img_fs[arr] + ((size_t)yp * g.tmp_w + xp) * C;
+  float* dst = const_cast<float*>(g.img[arr]) + (size_t)frame_of(g, f0, fr) * g.img_fs[arr] + ((size_t)yp * g.tmp_w + xp) * C;
   const int x = clampi(xp - g.pad, g.w), y = clampi(yp - g.pad, g.h);
   const float scale = __int_as_float((127 - 2 * sh) << 23);  // 4^-l
   int sum[3] = {0, 0, 0};
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) pyr_from_level_kernel(LevelGeom g, int f0
   const int fr = blockIdx.z >> 1, k = blockIdx.z & 1;
   const int C = g.noc, arr = k ? 3 : 0;
   const float* src = stage + ((size_t)fr * 2 + k) * ((size_t)g.w * g.h * C);
-  float* dst = const_cast<float*>(g.img[arr]) + (size_t)(f0 + fr) * g.img_fs[arr] + ((size_t)yp * g.tmp_w + xp) * C;
+  float* dst = const_cast<float*>(g.img[arr]) + (size_t)frame_of(g, f0, fr) * g.img_fs[arr] + ((size_t)yp * g.tmp_w + xp) * C;
   const int x = clampi(xp - g.pad, g.w), y = clampi(yp - g.pad, g.h);
   for (int c = 0; c < C; ++c) dst[c] = __ldg(src + ((size_t)y * g.w + x) * C + c);
 }
@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(LevelGeom gs, LevelGeom g
   if (xp >= gd.tmp_w || yp >= gd.tmp_h) return;
   const int fr = blockIdx.z >> 1, k = blockIdx.z & 1;
   const int C = gd.noc, arr = k ? 3 : 0;
-  const float* src = gs.img[arr] + (size_t)(f0 + fr) * gs.img_fs[arr];
-  float* dst = const_cast<float*>(gd.img[arr]) + (size_t)(f0 + fr) * gd.img_fs[arr] + ((size_t)yp * gd.tmp_w + xp) * C;
+  const float* src = gs.img[arr] + (size_t)frame_of(gd, f0, fr) * gs.img_fs[arr];
+  float* dst = const_cast<float*>(gd.img[arr]) + (size_t)frame_of(gd, f0, fr) * gd.img_fs[arr] + ((size_t)yp * gd.tmp_w + xp) * C;
   const int x = clampi(xp - gd.pad, gd.w), y = clampi(yp - gd.pad, gd.h);
   const float* r0 = src + ((size_t)(2 * y + gs.pad) * gs.tmp_w + (2 * x + gs.pad)) * C;
   const float* r1 = r0 + (size_t)gs.tmp_w * C;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(LevelGeom gs, LevelGeom g
 // come from 8-bit input every intermediate is exact, so this equals OpenCV bit for bit.
 __global__ void __launch_bounds__(256) sobel_kernel(LevelGeom g, int f0) {
   const int xp = blockIdx.x * blockDim.x + threadIdx.x, yp = blockIdx.y * blockDim.y + threadIdx.y;
-  const int frame = f0 + blockIdx.z;
+  const int frame = frame_of(g, f0, blockIdx.z);
   if (xp >= g.tmp_w || yp >= g.tmp_h) return;
   const int C = g.noc, w = g.w, h = g.h, P = g.pad;
   const float* im = g.img[0] + (size_t)frame * g.img_fs[0];
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) flow_upsample_kernel(LevelGeom g, int f0,
   const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y * blockDim.y + threadIdx.y;
   if (X >= w_org || Y >= h_org) return;
   const int fr = blockIdx.z;
-  const float* fl = g.flow + (size_t)(f0 + fr) * g.flow_frame_stride;
+  const float* fl = g.flow + (size_t)frame_of(g, f0, fr) * g.flow_frame_stride;
   float* o = out + ((size_t)fr * h_org * w_org + (size_t)Y * w_org + X) * NOP;
   const int s = 1 << g.level;
   if (s == 1) {

@@ -72,7 +72,7 @@ __device__ __forceinline__ float conv_v5(const float* q, int pitch, int h, int j
 template <int C, int NOP>
 __global__ void __launch_bounds__(256) warp_kernel(LevelGeom g, VarRefPlanes pl, int f0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int fr = blockIdx.z, frame = f0 + fr;
+  const int fr = blockIdx.z, frame = frame_of(g, f0, fr);
   if (i >= g.w || j >= g.h) return;
   const float* fl = g.flow + (size_t)frame * g.flow_frame_stride + ((size_t)j * g.w + i) * NOP;
   const float wx = fl[0], wy = (NOP == 2) ? fl[1] : 0.0f;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   constexpr int TH = TY * R;
   __shared__ float2 s_uv[TH + 4][TX + 4];
   __shared__ float s_s[TH + 2][TX + 2];
-  const int fr = blockIdx.z, frame = f0 + fr;
+  const int fr = blockIdx.z, frame = frame_of(g, f0, fr);
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TH;
   const int tid = threadIdx.y * TX + threadIdx.x;
   const int w = g.w, h = g.h, pitch = g.pitch;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
         uv.y = uv.y + dudv[b + 4 * hpad];
       } else {  // minps / maxps with zero (refine_variational.cpp:299-314)
         const float t = uv.x + dx;
-        uv.x = (g.camlr == 0) ? (t < 0.0f ? t : 0.0f) : (t > 0.0f ? t : 0.0f);
+        uv.x = (camlr_of(g, frame) == 0) ? (t < 0.0f ? t : 0.0f) : (t > 0.0f ? t : 0.0f);
       }
     }
     s_uv[cy][cx] = uv;
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     sor_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int f0, int K, int hpad) {
   extern __shared__ float4 s_pub[];  // [2][K][h+2][NF]
   constexpr int NF = (NOP == 2) ? 2 : 1;   // float4 per board entry: du x4, (dv x4)
-  const int fr = blockIdx.x, frame = f0 + fr;
+  const int fr = blockIdx.x, frame = frame_of(g, f0, fr);
   const int w = g.w, h = g.h;
   const int tid = threadIdx.x;
   // ---- helper warp: the last warp of the CTA only warms L1 -------------------------------------
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(MAXT, 1)
 template <int NOP>
 __global__ void __launch_bounds__(256) flow_update_kernel(LevelGeom g, VarRefPlanes pl, int f0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int fr = blockIdx.z, frame = f0 + fr;
+  const int fr = blockIdx.z, frame = frame_of(g, f0, fr);
   if (i >= g.w || j >= g.h) return;
   const float* dudv = reinterpret_cast<const float*>(pl.dudv + (size_t)fr * pl.dudv_stride);
   const size_t b = skew_f4(i >> 2, j, 0, 2, pl.hpad) * 4 + (i & 3);
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(256) flow_update_kernel(LevelGeom g, VarRefPla
     *reinterpret_cast<float2*>(f) = make_float2(wv.x + dudv[b], wv.y + dudv[b + 4 * pl.hpad]);
   } else {
     const float t = f[0] + dudv[b];
-    f[0] = (g.camlr == 0) ? (t < 0.0f ? t : 0.0f) : (t > 0.0f ? t : 0.0f);
+    f[0] = (camlr_of(g, frame) == 0) ? (t < 0.0f ? t : 0.0f) : (t > 0.0f ? t : 0.0f);
   }
 }
 

@@ -122,7 +122,8 @@ namespace {
 // with pyramid, gradients, paddings, upsampling and crop on the device (run_dense.cpp:130-178,
 // 298-311,407-414).
 struct RunIO {
-  const float **im_ao = nullptr, **im_ao_dx = nullptr, **im_ao_dy = nullptr, **im_bo = nullptr;
+  const float **im_ao = nullptr, **im_ao_dx = nullptr, **im_ao_dy = nullptr, **im_bo = nullptr, **im_bo_dx = nullptr,
+              **im_bo_dy = nullptr;
   const unsigned char* frames = nullptr;  // [2][height_org][width_org][noc]
   int width_org = 0, height_org = 0;
   float* outflow = nullptr;
@@ -145,9 +146,10 @@ void run_ofclass(const RunIO& io, const ofdis_params& p, int nop, int width, int
             "ofdis_upload_frames_u8");
     else
       for (int sl = sc_l; sl <= sc_f; ++sl)
-        check(ofdis_upload_level(ctx, 0, sl, io.im_ao[sl], io.im_ao_dx[sl], io.im_ao_dy[sl], io.im_bo[sl],
-                                 OFDIS_MEM_HOST),
-              ctx, "ofdis_upload_level");
+        check(ofdis_upload_level_fb(ctx, 0, sl, io.im_ao[sl], io.im_ao_dx[sl], io.im_ao_dy[sl], io.im_bo[sl],
+                                    io.im_bo_dx ? io.im_bo_dx[sl] : nullptr, io.im_bo_dy ? io.im_bo_dy[sl] : nullptr,
+                                    OFDIS_MEM_HOST),
+              ctx, "ofdis_upload_level_fb");
     if (io.initflow) check(ofdis_set_flow(ctx, 0, sc_f + 1, io.initflow, OFDIS_MEM_HOST), ctx, "ofdis_set_flow");
     if (verbosity > 1) {
       // per-level timing like oflow.cpp:303 (stages are timed with a stream sync each)
@@ -232,13 +234,13 @@ OFClass::OFClass(const float** im_ao_in, const float** im_ao_dx_in, const float*
                  const float tv_alpha_in, const float tv_gamma_in, const float tv_delta_in,
                  const int tv_innerit_in, const int tv_solverit_in, const float tv_sor_in,
                  const int verbosity_in, const int nop_in, const int device) {
-  (void)im_bo_dx_in;
-  (void)im_bo_dy_in;  // never read by the reference either (patch.cpp:90-97)
   RunIO io;
   io.im_ao = im_ao_in;
   io.im_ao_dx = im_ao_dx_in;
   io.im_ao_dy = im_ao_dy_in;
   io.im_bo = im_bo_in;
+  io.im_bo_dx = im_bo_dx_in;  // only the forward-backward grid reads them (oflow.cpp:193-197)
+  io.im_bo_dy = im_bo_dy_in;
   io.outflow = outflow;
   io.initflow = initflow;
   run_ofclass(io,
@@ -291,7 +293,7 @@ PatGridClass::PatGridClass(const camparam* cpt_in, const camparam* cpo_in, const
 PatGridClass::~PatGridClass() { ofdis_destroy(ctx); }
 
 void PatGridClass::SetComplGrid(PatGridClass*) {
-  throw std::runtime_error("PatGridClass::SetComplGrid: forward-backward merge (usefbcon) is not built");
+  throw std::runtime_error("PatGridClass::SetComplGrid: the forward-backward merge runs inside the engine; use OFClass with usefbcon=1");
 }
 
 void PatGridClass::InitializeGrid(const float* a, const float* ax, const float* ay) {

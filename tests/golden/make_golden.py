@@ -27,12 +27,19 @@ CASES = {
     "gray_stereo": (96, 224, 1, "3 1 24 24 0.05 0.95 0 12 0.75 0 1 0 1 10 10 5 1 3 1.6 0", 1, 4.0, True),
     "gray_flow_earlyexit": (100, 168, 1, "3 1 16 2 0.05 0.95 0.5 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0", 2, 5.0, False),
     "gray_flow_big_motion": (128, 256, 1, "3 1 12 12 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0", 2, 40.0, False),
+    # forward-backward consistency (README parameter 10 = 1): second grid on the swapped images
+    "gray_flow_fbcon": (120, 200, 1, "3 1 8 8 0.05 0.95 0 8 0.4 1 1 0 1 10 10 5 1 3 1.6 0", 2, 6.0, False),
+    "rgb_flow_fbcon_l1cost": (104, 184, 3, "3 1 8 8 0.05 0.95 0 12 0.75 1 1 1 1 10 10 5 1 3 1.6 0", 2, 4.0, False),
+    "gray_stereo_fbcon": (96, 224, 1, "3 1 12 12 0.05 0.95 0 8 0.4 1 1 0 1 10 10 5 1 3 1.6 0", 1, 4.0, True),
 }
 
 
 def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]  # optional: generate just these fixtures
     for name, (h, w, ch, cli, nop, amp, stereo) in CASES.items():
+        if only and name not in only:
+            continue
         prm = params.from_cli_numbers(cli.split(), noc=ch, nop=nop)
         i0, i1, _ = synth.synthetic_pair(h, w, ch, seed=len(name), amp=amp, stereo=stereo)
         pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)

@@ -77,6 +77,9 @@ def test_host_classes_selftest(bindir):
     ("run_OF_INT", 1, 2, [], "pgm"),
     ("run_OF_RGB", 3, 2, "3 1 16 16 0.05 0.95 0 12 0.75 0 1 1 1 10 10 5 1 3 1.6 0".split(), "png"),
     ("run_DE_INT", 1, 1, "3 1 24 24 0.05 0.95 0 12 0.75 0 1 0 1 10 10 5 1 3 1.6 0".split(), "pgm"),
+    # README parameter 10 (usefbcon) = 1: forward-backward consistency
+    ("run_OF_INT", 1, 2, "3 1 8 8 0.05 0.95 0 8 0.4 1 1 0 1 10 10 5 1 3 1.6 0".split(), "pgm"),
+    ("run_DE_RGB", 3, 1, "3 1 8 8 0.05 0.95 0 8 0.4 1 1 0 1 10 10 5 1 3 1.6 0".split(), "png"),
 ])
 def test_cli_output_equals_python_pipeline(tmp_path, bindir, oracle_port, exe, ch, nop, args, fmt):
     h, w = (150, 250) if len(args) > 1 else (218, 500)  # not divisible by 2^lv_f: exercises the padding/crop

@@ -56,7 +56,14 @@ def test_golden_fixtures_whole_run_and_patch_stage(path, api):
     ctx.upload_pyramids(0, pyr)
     ctx.run(1)
     assert_bits(ctx.get_flow(0, prm.sc_l), z["flow"], "flow")
-    # patch stage of the finest level from a prescribed coarser flow
+    # patch stage of the finest level from a prescribed coarser flow (the stage fixture is the plain
+    # grid: without the forward-backward merge)
+    if prm.usefbcon:
+        ctx.close()
+        import dataclasses
+        prm = dataclasses.replace(prm, usefbcon=0)
+        ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+        ctx.upload_pyramids(0, pyr)
     lv = prm.sc_l
     ctx.set_flow(0, lv + 1, z["flow_prev"])
     ctx.patgrid_optimize(lv, 0, 1, True)
@@ -327,4 +334,47 @@ def test_full_size_stereo_op4_vs_oracle(api, oracle_port):
     ctx.upload_pyramids(0, pyr)
     ctx.run(1)
     assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "cfg5 run")
+    ctx.close()
+
+
+FB_CASES = [
+    (2, 1, "3 1 8 8 0.05 0.95 0 8 0.4 1 1 0 1 10 10 5 1 3 1.6 0", (120, 200), 3.0),
+    (1, 1, "3 1 8 8 0.05 0.95 0 8 0.4 1 1 0 1 10 10 5 1 3 1.6 0", (120, 200), 3.0),
+    (2, 3, "4 2 6 4 0.05 0.95 0 12 0.75 1 1 1 1 10 10 5 1 3 1.6 0", (144, 208), 3.0),
+    (1, 3, "3 0 6 4 0.05 0.95 0 8 0.5 1 0 2 0 10 10 5 1 3 1.6 0", (64, 96), 3.0),
+    (2, 1, "3 1 8 8 0.05 0.95 0 8 0.4 1 1 0 1 10 10 5 1 3 1.6 0", (120, 200), 14.0),
+    (2, 1, "2 2 8 8 0.05 0.95 0 8 0.4 1 1 0 1 10 10 5 1 3 1.6 0", (64, 96), 2.0),   # one level only
+]
+
+
+@pytest.mark.parametrize("nop,ch,numbers,size,amp", FB_CASES)
+def test_forward_backward_consistency_vs_oracle(nop, ch, numbers, size, amp, api, oracle_port):
+    """usefbcon = 1 (README parameter 10): second grid on the swapped images, merged densification
+    (patchgrid.cpp:278-375), backward refinement on all but the last level -- bitwise against the oracle,
+    for a batch of pairs and through the image-only upload (backward gradients derived on the device)."""
+    prm = params.from_cli_numbers(numbers.split(), noc=ch, nop=nop)
+    nfr = 2
+    pyrs = []
+    for s in range(nfr):
+        i0, i1, _ = synth.synthetic_pair(size[0], size[1], ch, seed=50 + s, stereo=(nop == 1), amp=amp)
+        pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
+    exp = [oracle_port.port_run(p, prm) for p in pyrs]
+    ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, nfr)
+    for f, p in enumerate(pyrs):
+        ctx.upload_pyramids(f, p)
+    ctx.run(nfr)
+    for f in range(nfr):
+        assert_bits(ctx.get_flow(f, prm.sc_l), exp[f], "frame %d" % f)
+    # graph replay + finest-level upload: the device builds both directions' pyramids and gradients
+    P, l = pyrs[0].imgpadding, prm.sc_l
+    packed = np.ascontiguousarray(np.stack([np.stack([p.i0[l][P:-P, P:-P], p.i1[l][P:-P, P:-P]]) for p in pyrs]))
+    ctx.upload_finest_level(0, nfr, packed)
+    ctx.set_graph_mode(True)
+    ctx.run(nfr)
+    ctx.run(nfr)
+    out = np.empty((nfr,) + exp[0].shape, np.float32)
+    ctx.get_flow_batch(0, nfr, out)
+    ctx.sync()
+    for f in range(nfr):
+        assert_bits(out[f], exp[f], "graph + finest-level upload, frame %d" % f)
     ctx.close()
