@@ -97,7 +97,7 @@ class PatGridClass {
   void InitializeFromCoarserOF(const float* flow_prev);
   void AggregateFlowDense(float* flowout) const;
   void Optimize();
-  void SetComplGrid(PatGridClass* cg_in);  // forward-backward merge: not built (throws)
+  void SetComplGrid(PatGridClass* cg_in);  // throws: the merge runs inside the engine (OFClass, usefbcon=1)
   inline int GetNoPatches() const { return nopatches; }
   inline int GetNoph() const { return noph; }
   inline int GetNopw() const { return nopw; }
