@@ -409,13 +409,7 @@ __device__ __forceinline__ float4 ldg128(const float4* p) {
 }
 __device__ __forceinline__ float4 ldg128_rw(const float4* p) {  // data written earlier in this kernel family
   float4 v;
-#if defined(OFDIS_RW_NC)
-  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-#elif defined(OFDIS_RW_CG)
-  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-#else
   asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-#endif
   return v;
 }
 __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
@@ -657,6 +651,7 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   const int tma_threads = K * hpad + 32;
   const size_t tma_smem = (size_t)sor_tma_stages(K) * ((NOP == 2 ? 8 : 5) + 2) * hpad * 16 +
                           sizeof(float4) * 2 * (size_t)K * (g.h + 2) * nf4 + 8 * (size_t)sor_tma_stages(K);
+  // tuning knob of tools/lanes_probe.py: a larger request limits how many SOR CTAs share an SM
   static const long exp_min_smem = getenv("OFDIS_EXP_SOR_SMEM_KB") ? atol(getenv("OFDIS_EXP_SOR_SMEM_KB")) * 1024 : 0;
   const size_t tma_smem_req = tma_smem < (size_t)exp_min_smem ? (size_t)exp_min_smem : tma_smem;
   const bool use_tma = (K >= 1) && tma_threads <= 288 && tma_smem <= 200 * 1024 &&
