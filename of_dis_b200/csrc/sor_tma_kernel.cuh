@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(288, 1)
   const float omega = vp.omega;
   const unsigned lane_off = (unsigned)j * 16u, rowb = (unsigned)hpad * 16u;
   const unsigned jb_off = (unsigned)((j + 1 < hpad) ? j + 1 : j) * 16u;  // row below, same diagonal row
+  const int jw_lo = jraw & ~31, jw_hi = (jw_lo + 31 < h - 1) ? jw_lo + 31 : h - 1;  // rows of this warp
   const int tstart = j + 2 * k;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float du_l = 0.f, dv_l = 0.f, hl = 0.f;
@@ -217,6 +218,11 @@ __global__ void __launch_bounds__(288, 1)
     SOR_STAMP(0, omega, omega);
     const int n = T - 2 * k;  // load number == diagonal of this warp's blocks
     SOR_STAMP(1, omega, omega);
+    // Warp-uniform: does any row of this warp hold a block this super-step, or start one in the
+    // next (that lane must fetch its previous-sweep block now)?  Rows jw_lo..jw_hi, block I = n - j,
+    // wanted -1 <= I < W4.  Idle warps (the ramp-up and ramp-down of the wavefront, 28 % of the
+    // warp-steps on a 128x54 level) only keep the ring and board indices moving.
+    if (jw_lo <= n + 1 && jw_hi > n - W4) {
     const unsigned sa = sbase + st * stage_bytes;
     float4 F[NQ];
 #pragma unroll
@@ -270,7 +276,8 @@ __global__ void __launch_bounds__(288, 1)
       own_u = nxt_u;
       own_v = nxt_v;
     }
-    SOR_STAMP(5, nu[0], nu[1]);
+    }
+    SOR_STAMP(5, omega, omega);
     __syncthreads();
     SOR_STAMP(6, omega, omega);
     const unsigned tmp = prevb;

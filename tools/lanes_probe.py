@@ -3,10 +3,13 @@ import sys, time
 sys.path.insert(0, '/root/repo')
 import torch
 from of_dis_b200 import api, params, preprocess, synth
+import dataclasses, os
 prm = params.operating_point(2, 1024)
+FB = int(os.environ.get('FB', '0'))  # 1: forward-backward consistency (usefbcon)
+prm = dataclasses.replace(prm, usefbcon=FB)
 i0, i1, _ = synth.synthetic_pair(436, 1024, 1, seed=0)
 pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
-B = 64; NL = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+B = int(os.environ.get('B', '64')); NL = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 lanes = []
 for _ in range(NL):
     st = torch.cuda.Stream()
@@ -14,8 +17,10 @@ for _ in range(NL):
     lanes.append((c, st))
 import numpy as np
 packed = np.stack([lanes[0][0].pack_frame(pyr)] * B)
+ni = lanes[0][0].packed_images_frame_floats
+imgs = np.ascontiguousarray(packed[:, :ni])
 for c, st in lanes:
-    c.upload_packed(0, B, packed); c.set_graph_mode(True); c.run(B)
+    c.upload_packed_images(0, B, imgs); c.set_graph_mode(True); c.run(B)
 torch.cuda.synchronize()
 def pipelined(steps=80):
     for i in range(2 * NL): lanes[i % NL][0].run(B)
@@ -29,4 +34,4 @@ def pipelined(steps=80):
     e1.record(s0); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / steps
 r = [pipelined() for _ in range(3)]
-print('lanes %d: ms/step %s -> %.1f Gpix/s' % (NL, ['%.4f' % x for x in r], B * 436 * 1024 / min(r) / 1e6))
+print('B %d' % B, 'usefbcon %d' % FB, 'lanes %d: ms/step %s -> %.1f Gpix/s' % (NL, ['%.4f' % x for x in r], B * 436 * 1024 / min(r) / 1e6))
