@@ -344,6 +344,7 @@ FB_CASES = [
     (1, 3, "3 0 6 4 0.05 0.95 0 8 0.5 1 0 2 0 10 10 5 1 3 1.6 0", (64, 96), 3.0),
     (2, 1, "3 1 8 8 0.05 0.95 0 8 0.4 1 1 0 1 10 10 5 1 3 1.6 0", (120, 200), 14.0),
     (2, 1, "2 2 8 8 0.05 0.95 0 8 0.4 1 1 0 1 10 10 5 1 3 1.6 0", (64, 96), 2.0),   # one level only
+    (2, 1, "5 3 12 12 0.05 0.95 0 8 0.4 1 1 0 1 10 10 5 1 3 1.6 0", (436, 1024), 6.0),  # operating point 2 of cfg 2 + fbcon
 ]
 
 
@@ -377,4 +378,45 @@ def test_forward_backward_consistency_vs_oracle(nop, ch, numbers, size, amp, api
     ctx.sync()
     for f in range(nfr):
         assert_bits(out[f], exp[f], "graph + finest-level upload, frame %d" % f)
+    ctx.close()
+
+
+def _random_config(rng):
+    """A valid parameter set / image size drawn from the ranges the reference's CLI accepts."""
+    P = int(rng.choice([4, 6, 8, 10, 12, 16]))
+    ch = int(rng.choice([1, 3]))
+    nop = int(rng.choice([1, 2]))
+    nlev = int(rng.integers(1, 4))
+    sc_l = int(rng.integers(0, 3))
+    sc_f = sc_l + nlev - 1
+    mult = 1 << sc_f
+    # coarsest level at least 6 x 8 pixels, finest level at most ~160 x 200
+    h = int(rng.integers(max(6, 40 >> sc_l), max(8, 160 >> sc_l) + 1)) << sc_l
+    w = int(rng.integers(max(8, 48 >> sc_l), max(10, 200 >> sc_l) + 1)) << sc_l
+    h, w = (h + mult - 1) // mult * mult, (w + mult - 1) // mult * mult
+    max_iter = int(rng.integers(1, 20))
+    min_iter = int(rng.integers(0, max_iter + 1))
+    numbers = [sc_f, sc_l, max_iter, min_iter, float(rng.choice([0.05, 0.2, 0.5])), float(rng.choice([0.95, 0.8, 0.5])),
+               float(rng.choice([0.0, 0.5, 2.0])), P, float(rng.choice([0.0, 0.3, 0.4, 0.5, 0.75, 0.9])),
+               int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(0, 3)), int(rng.integers(0, 2)),
+               float(rng.choice([10.0, 3.0, 30.0])), float(rng.choice([10.0, 0.0, 5.0])), float(rng.choice([5.0, 0.0, 12.0])),
+               int(rng.integers(1, 3)), int(rng.integers(1, 6)), float(rng.choice([1.6, 1.0, 1.9])), 0]
+    return numbers, ch, nop, (h, w), float(rng.choice([1.0, 4.0, 12.0]))
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_configurations_vs_oracle(seed, api, oracle_port):
+    """Seeded sweep over the parameter space (patch sizes 4..16, overlaps 0..0.9, 1..3 levels, early
+    exit thresholds, all three costs, patnorm on/off, refinement on/off with varied weights and sweep
+    counts, gray/RGB, flow/stereo, forward-backward on/off): whole run, bitwise against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    numbers, ch, nop, size, amp = _random_config(rng)
+    prm = params.from_cli_numbers(numbers, noc=ch, nop=nop)
+    i0, i1, _ = synth.synthetic_pair(size[0], size[1], ch, seed=200 + seed, stereo=(nop == 1), amp=amp)
+    pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
+    exp = oracle_port.port_run(pyr, prm)
+    ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    ctx.upload_pyramids(0, pyr)
+    ctx.run(1)
+    assert_bits(ctx.get_flow(0, prm.sc_l), exp, "config %s ch=%d nop=%d size=%s" % (numbers, ch, nop, size))
     ctx.close()
