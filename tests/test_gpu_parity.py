@@ -389,11 +389,10 @@ def _random_config(rng):
     nlev = int(rng.integers(1, 4))
     sc_l = int(rng.integers(0, 3))
     sc_f = sc_l + nlev - 1
-    mult = 1 << sc_f
-    # coarsest level at least 6 x 8 pixels, finest level at most ~160 x 200
-    h = int(rng.integers(max(6, 40 >> sc_l), max(8, 160 >> sc_l) + 1)) << sc_l
-    w = int(rng.integers(max(8, 48 >> sc_l), max(10, 200 >> sc_l) + 1)) << sc_l
-    h, w = (h + mult - 1) // mult * mult, (w + mult - 1) // mult * mult
+    # coarsest level 6..24 x 8..30 pixels (the reference's 5-tap vertical filter reads out of bounds
+    # below 4 rows, image.c:401-434); the finest level stays below ~100 x 120
+    h = int(rng.integers(6, 25 >> (nlev - 1)) + 1) << sc_f if (25 >> (nlev - 1)) > 6 else 6 << sc_f
+    w = int(rng.integers(8, max(9, 31 >> (nlev - 1)) + 1)) << sc_f
     max_iter = int(rng.integers(1, 20))
     min_iter = int(rng.integers(0, max_iter + 1))
     numbers = [sc_f, sc_l, max_iter, min_iter, float(rng.choice([0.05, 0.2, 0.5])), float(rng.choice([0.95, 0.8, 0.5])),
