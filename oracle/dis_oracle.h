@@ -4,7 +4,7 @@
  * form the CUDA kernels use.  It is the checker for tests/, smoke() and the
  * "port" CPU baseline of bench.py; the product never links or imports it.
  *
- * Pinned: tests/test_oracle_vs_ref.py requires BITWISE equality with
+ * Pinned: tests/test_oracle.py requires BITWISE equality with
  * oracle/_ref (the reference's own sources compiled in place) on every stage
  * and on whole runs; small golden fixtures of those runs live in tests/golden/.
  * Unpinned boundary: Eigen's reduction order (see oracle/eigen_shim/Eigen/Core).
