@@ -1,6 +1,6 @@
 /* ofdis_b200.h -- C-ABI of the B200-native DIS optical-flow hot path.
  *
- * This is the drop-in boundary (DESIGN.md section 2): plain C, plain pointers
+ * This is the drop-in boundary (DESIGN.md section 1): plain C, plain pointers
  * and sizes, no C++/torch types.  Everything the reference's three classes do
  * on the hot path is reachable from here:
  *
@@ -14,6 +14,8 @@
  *   PatGridClass::Optimize           patchgrid.cpp:134-141  ofdis_patgrid_optimize
  *     (PatClass::InitializePatch, OptimizeIter  patch.cpp:57-88,119-212 -- fused into the same kernel)
  *   PatGridClass::AggregateFlowDense patchgrid.cpp:213-397  ofdis_patgrid_aggregate
+ *   PatGridClass::SetComplGrid       patchgrid.h:36 + oflow.cpp:162-170   ofdis_params.usefbcon = 1 (both grids of a pair
+ *                                                            live in the context; ofdis_upload_level_fb)
  *   PatGridClass::GetQuePatchDis &c  patchgrid.h:42-44      ofdis_get_patches
  *   VarRefClass::VarRefClass         refine_variational.h:37-39,    ofdis_varref_refine
  *                                    refine_variational.cpp:25-116
@@ -66,7 +68,7 @@ enum {
   OFDIS_OK = 0,
   OFDIS_ERR_ARG = -1,         /* bad argument / unsupported geometry */
   OFDIS_ERR_CUDA = -2,        /* a CUDA call failed; see ofdis_last_error */
-  OFDIS_ERR_UNSUPPORTED = -3, /* valid in the reference but not built here (levels taller than 1024 rows) */
+  OFDIS_ERR_UNSUPPORTED = -3, /* valid in the reference but not built here (levels taller than 1024 rows; ofdis_upload_packed with usefbcon) */
   OFDIS_ERR_NOMEM = -4
 };
 enum { OFDIS_MEM_HOST = 0, OFDIS_MEM_DEVICE = 1 };
@@ -83,7 +85,8 @@ const char* ofdis_version(void);
 
 /* camparam::camlr (oflow.h:28; 0 = left/forward grid clamps disparity <= 0, 1 = right/backward
  * clamps >= 0, patch.cpp:188-193, refine_variational.cpp:299-314).  Default 0, as OFClass's
- * forward grid uses.  Only meaningful for nop == 1. */
+ * forward grid uses.  Only meaningful for nop == 1; with usefbcon the forward grid is 0 and the
+ * backward grid 1 whatever is set here. */
 int ofdis_set_camlr(ofdis_ctx* ctx, int camlr);
 /* optparam::dp_thresh is stored SQUARED by OFClass (oflow.cpp:88); callers that already hold
  * the squared value (PatGridClass built from an optparam) set it here bit-exactly. */
@@ -94,8 +97,8 @@ int ofdis_level_info(const ofdis_ctx* ctx, int level, int* w, int* h, int* nopw,
 
 /* Images of one level of one frame pair: padded, row-major, channel-interleaved
  * float32, (h+2*pad) x (w+2*pad) x noc, exactly what OFClass receives
- * (oflow.h:84-86).  The gradients of I1 are never read by the reference
- * (patch.cpp:90-97) and are not part of this interface. */
+ * (oflow.h:84-86).  The gradients of I1 are only read by the forward-backward grid
+ * (oflow.cpp:193-197); without usefbcon they are not needed (ofdis_upload_level_fb otherwise). */
 int ofdis_upload_level(ofdis_ctx* ctx, int frame, int level, const float* i0, const float* i0x,
                        const float* i0y, const float* i1, int memkind);
 
@@ -107,7 +110,8 @@ int ofdis_upload_level_fb(ofdis_ctx* ctx, int frame, int level, const float* i0,
 
 /* Packed transfer: all levels sc_f..sc_l of frames [f0,f1) in the context's own
  * layout (per frame: I0,I1 of levels sc_f..sc_l, then I0x,I0y of the same levels; use
- * ofdis_packed_offset), one copy. */
+ * ofdis_packed_offset), one copy.  Not available with usefbcon (a packed frame has no gradients of
+ * the second image: OFDIS_ERR_UNSUPPORTED); the image-only transfers below are. */
 size_t ofdis_packed_frame_floats(const ofdis_ctx* ctx);
 size_t ofdis_packed_offset(const ofdis_ctx* ctx, int level, int which /*0 I0,1 I0x,2 I0y,3 I1*/);
 int ofdis_upload_packed(ofdis_ctx* ctx, int f0, int f1, const float* packed, int memkind);
