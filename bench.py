@@ -195,12 +195,17 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="pairs per GPU per step")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--lanes", type=int, default=8, help="contexts/streams whose steps overlap")
+    ap.add_argument("--lanes", type=int, default=0,
+                    help="contexts/streams whose steps overlap; 0 = 8, or the divisor of --steps in 6..12 closest to 8 "
+                         "(every lane then runs the same number of steps and the drain is shortest)")
     ap.add_argument("--e2e-upload", choices=("finest", "images", "pyramids"), default="finest",
                     help="e2e H2D payload: I0,I1 of the finest used level (coarser levels, gradients and paddings derived "
                          "on the device), I0,I1 of every level, or all four arrays of every level as OFClass takes them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.lanes <= 0:
+        divs = [d for d in range(6, 13) if args.steps % d == 0]
+        args.lanes = min(divs, key=lambda d: (abs(d - 8), -d)) if divs else 8
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
