@@ -452,6 +452,8 @@ def main():
                 c2.run(b)
                 c2.get_flow_batch(0, b, host_out.data_ptr())
 
+            for _ in range(3):  # the first upload allocates the context's staging buffer
+                e2e_b()
             ms2 = timed(e2e_b, 10)
             sweep[str(b)] = {"ms_per_step": ms, "value": b * H_ORG * W_ORG / (ms * 1e-3) / 1e6,
                              "e2e_ms_per_step": ms2, "e2e_value": b * H_ORG * W_ORG / (ms2 * 1e-3) / 1e6}
