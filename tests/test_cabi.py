@@ -50,3 +50,24 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(api, "LIB_PATH", "/nonexistent/libofdis_b200.so")
     with pytest.raises(api.OfdisError):
         api.lib()
+
+
+def test_reference_arm_prints_the_contract_line(tmp_path):
+    """bench.py --impl reference (the reference CPU build, or the oracle port when /root/reference is absent)
+    prints one JSON line with the keys the driver reads."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--batch", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
