@@ -10,10 +10,15 @@ of BASELINE configs[3]; one pair alone leaves 147 of 148 SMs idle, see
 batch_sweep in the output).  Pixels are counted at the ORIGINAL image size, once
 per pair.
 
-  value : device-timed, padded pyramids already resident in HBM
-  e2e   : same metric through the C-ABI with pinned HOST buffers; H2D of the
-          packed pyramids and D2H of the flows inside the timed region
-  roofline     : dominant kernel (lexicographic SOR), algorithmic bytes / CUDA-event time
+  value : device-timed, padded pyramids already resident in HBM; the K steps are dealt round-robin
+          to 8-10 lanes (context + stream) so that consecutive steps overlap
+  e2e   : same metric through the C-ABI with pinned HOST buffers; every step copies its input
+          (default: the un-padded finest-level images, the rest of the pyramid is derived on the
+          device inside the timed region; --e2e-upload pyramids ships what OFClass takes) and its
+          flows; the result is checked bit for bit against the resident path
+  single_lane / batch_sweep : one lane, L2 flushed before every step (latency of 64, 8, 1 pairs)
+  roofline     : dominant kernel (lexicographic SOR), algorithmic bytes / CUDA-event time, plus the
+                 issue-slot utilisation of the whole overlapped step
   cpu_baseline : the reference CPU build (oracle/_ref) or the C port on this box's cores
 
 Under torchrun every rank owns B pairs (weak scaling, no data-path collective;
