@@ -221,8 +221,10 @@ __global__ void __launch_bounds__(288, 1)
     // Warp-uniform: does any row of this warp hold a block this super-step, or start one in the
     // next (that lane must fetch its previous-sweep block now)?  Rows jw_lo..jw_hi, block I = n - j,
     // wanted -1 <= I < W4.  Idle warps (the ramp-up and ramp-down of the wavefront, 28 % of the
-    // warp-steps on a 128x54 level) only keep the ring and board indices moving.
-    if (jw_lo <= n + 1 && jw_hi > n - W4) {
+    // warp-steps on a 128x54 level) only keep the ring and board indices moving.  Warps made of
+    // shadow lanes only (rows >= h; possible when hpad = 128) never run the body: joining late they
+    // would carry a wrong left-neighbour state into the board slot shared with the real last row.
+    if (jw_lo < h && jw_lo <= n + 1 && jw_hi > n - W4) {
     const unsigned sa = sbase + st * stage_bytes;
     float4 F[NQ];
 #pragma unroll

@@ -529,9 +529,17 @@ __global__ void __launch_bounds__(MAXT, 1)
   unsigned prevb = bufbytes, curb = 0;   // T even: write buffer 0, read buffer 1
 
   // one super-step: `cur` holds block I, `nxt` block I+1
+  // Rows of this warp.  A warp none of whose rows is within 3 super-steps of holding a block (the
+  // register sets are filled two steps ahead, the previous-sweep hand-over one step ahead) skips
+  // the body: on a 1440x1024 level only ~12 of the 32 warps are inside the wavefront at a time.
+  // Warps made of shadow lanes only (rows >= h) never run it: a shadow lane that joined late would
+  // carry a wrong left-neighbour state into the board slot it shares with the real last row.
+  const int jw_lo = jraw & ~31, jw_hi = (jw_lo + 31 < h - 1) ? jw_lo + 31 : h - 1;
   auto step = [&](SorSet& cur, SorSet& nxt, int I, int T) {
     const bool in_range = valid & (I >= 0) & (I < W4);
     SOR_STAMP(0, omega, omega);
+    const int n = T - 2 * k;
+    if (jw_lo < h && jw_lo <= n + 3 && jw_hi > n - W4) {
     if (!k0) {  // previous-sweep values come from the board (written one super-step ago)
       nxt.own_u = lds128(a_right + prevb);
       cur.bot_u = lds128(a_bot + prevb);
@@ -562,7 +570,8 @@ __global__ void __launch_bounds__(MAXT, 1)
       dst[0] = make_float4(nu[0], nu[1], nu[2], nu[3]);
       if (NOP == 2) dst[hpad] = make_float4(nv[0], nv[1], nv[2], nv[3]);
     }
-    SOR_STAMP(5, nu[0], nu[1]);
+    }
+    SOR_STAMP(5, omega, omega);
     __syncthreads();
     SOR_STAMP(6, omega, omega);
     const unsigned tmp = prevb;

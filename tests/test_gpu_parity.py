@@ -90,6 +90,13 @@ CASES = {
         "3 1 8 8 0.05 0.95 0 6 0.5 0 0 0 1 10 10 5 2 5 1.5 0".split()), 6.0, False),
     "gray_early_exit": (200, 320, 1, lambda: params.from_cli_numbers(
         "3 1 16 2 0.05 0.95 0.5 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split()), 6.0, False),
+    # 2 SOR sweeps on a 70-row level: rows padded to 128, so one warp of every sweep holds shadow
+    # lanes only (the TMA kernel with HPAD = 128)
+    "gray_sor2_rows70": (140, 352, 1, lambda: params.from_cli_numbers(
+        "2 1 8 8 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 2 2 1.6 0".split()), 6.0, False),
+    # 1 sweep, 100 rows, wide
+    "stereo_sor1_rows100": (200, 416, 1, lambda: params.from_cli_numbers(
+        "2 1 8 8 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 1 1.8 0".split(), noc=1, nop=1), 6.0, True),
 }
 
 
