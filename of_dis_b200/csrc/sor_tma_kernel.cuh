@@ -122,7 +122,7 @@ __host__ __device__ inline int sor_tma_stages(int K) { return 2 * K + SOR_TMA_PF
 // HPAD (rows padded to 32/64/128/256) is a template parameter so that every shared-memory
 // address is `base + immediate`; stage indices advance incrementally (no modulo in the loop).
 template <int NOP, int HPAD>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(HPAD <= 64 ? 288 : 448, 1)  // HPAD 128: up to 3 sweeps x 128 rows + producer warp
     sor_tma_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int K) {
   constexpr int hpad = HPAD;
   extern __shared__ __align__(128) float4 s_dyn[];

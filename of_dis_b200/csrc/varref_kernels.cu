@@ -655,15 +655,17 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
     else if (variant == 1) cudaFuncSetAttribute(sor_kernel<NOP, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     else cudaFuncSetAttribute(sor_kernel<NOP, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
-  // TMA-producer variant when all sweeps fit one CTA of <= 288 threads and the stage ring fits
-  // shared memory (the common case: level heights up to 85 rows with 3 sweeps)
+  // TMA-producer variant when all sweeps fit one CTA (<= 288 threads; 448 when rows are padded to
+  // 128) and the stage ring fits shared memory: level heights up to 128 rows with 3 sweeps
   const int tma_threads = K * hpad + 32;
   const size_t tma_smem = (size_t)sor_tma_stages(K) * ((NOP == 2 ? 8 : 5) + 2) * hpad * 16 +
                           sizeof(float4) * 2 * (size_t)K * (g.h + 2) * nf4 + 8 * (size_t)sor_tma_stages(K);
   // tuning knob of tools/lanes_probe.py: a larger request limits how many SOR CTAs share an SM
   static const long exp_min_smem = getenv("OFDIS_EXP_SOR_SMEM_KB") ? atol(getenv("OFDIS_EXP_SOR_SMEM_KB")) * 1024 : 0;
   const size_t tma_smem_req = tma_smem < (size_t)exp_min_smem ? (size_t)exp_min_smem : tma_smem;
-  const bool use_tma = (K >= 1) && tma_threads <= 288 && tma_smem <= 200 * 1024 &&
+  // thread budget: 288 (<= 3 sweeps x 64 rows, 2 x 128, 1 x 256) or, for rows padded to 128, 448
+  static const bool exp_no_tma128 = getenv("OFDIS_EXP_NO_TMA128") != nullptr;  // A/B knob of tools/hd_probe.py (1920x1080: 1.32 -> 0.63 ms per 16 pairs)
+  const bool use_tma = (K >= 1) && tma_threads <= ((hpad == 128 && !exp_no_tma128) ? 448 : 288) && tma_smem <= 220 * 1024 &&
                        (hpad == 32 || hpad == 64 || hpad == 128 || hpad == 256);
   auto launch_tma = [&]() {
 #define SOR_TMA_LAUNCH(HP)                                                                             \
