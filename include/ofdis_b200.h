@@ -68,7 +68,7 @@ enum {
   OFDIS_OK = 0,
   OFDIS_ERR_ARG = -1,         /* bad argument / unsupported geometry */
   OFDIS_ERR_CUDA = -2,        /* a CUDA call failed; see ofdis_last_error */
-  OFDIS_ERR_UNSUPPORTED = -3, /* valid in the reference but not built here (levels taller than 1024 rows; ofdis_upload_packed with usefbcon) */
+  OFDIS_ERR_UNSUPPORTED = -3, /* valid in the reference but not built here (refinement levels taller than 256 rows x the largest thread-block cluster, i.e. 2048 or 4096 rows; ofdis_upload_packed with usefbcon) */
   OFDIS_ERR_NOMEM = -4
 };
 enum { OFDIS_MEM_HOST = 0, OFDIS_MEM_DEVICE = 1 };
@@ -182,6 +182,14 @@ long ofdis_launch_count(const ofdis_ctx* ctx);
  * {0 patch, 1 densify, 2 refinement setup (warp+derivatives), 3 assemble, 4 SOR} into
  * ms_by_class[5] / launches_by_class[5] (launch groups, one per stage call). */
 int ofdis_profile_run(ofdis_ctx* ctx, int nframes, int steps, double* ms_by_class, long* launches_by_class);
+/* The same, additionally split by pyramid level: ms_by_level_class[(level - sc_l) * 5 + class] (may be NULL). */
+int ofdis_profile_levels(ofdis_ctx* ctx, int nframes, int steps, double* ms_by_class, long* launches_by_class,
+                         double* ms_by_level_class);
+/* Launch-geometry options (tuning / test hook, results are bit-identical under every setting):
+ *   "sor_single_max"  32 | 64 | 128 (default): refinement levels of up to this many rows run their SOR in
+ *                     one CTA, taller ones in a thread-block cluster of row bands (sor_wave_kernel.cuh)
+ *   "sor_max_cluster" 8 (portable, default unless the finest level needs more) | 16 */
+int ofdis_set_option(ofdis_ctx* ctx, const char* name, int value);
 /* CUDA-graph replay of ofdis_run (captured on first use per nframes). */
 int ofdis_set_graph_mode(ofdis_ctx* ctx, int enabled);
 

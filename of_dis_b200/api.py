@@ -30,7 +30,7 @@ EXPORTS = [
     "ofdis_debug_varref_iters", "ofdis_launch_count", "ofdis_set_graph_mode", "ofdis_profile_run",
     "ofdis_set_camlr", "ofdis_set_dp_thresh_sq", "ofdis_packed_images_frame_floats", "ofdis_upload_packed_images",
     "ofdis_upload_frames_u8", "ofdis_finest_level_frame_floats", "ofdis_upload_finest_level", "ofdis_get_flow_fullres",
-    "ofdis_get_level", "ofdis_upload_level_fb",
+    "ofdis_get_level", "ofdis_upload_level_fb", "ofdis_set_option", "ofdis_profile_levels",
 ]
 
 
@@ -89,9 +89,11 @@ def lib():
         L.ofdis_get_patches.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4
         L.ofdis_debug_get.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
         L.ofdis_set_graph_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.ofdis_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
         L.ofdis_set_camlr.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.ofdis_set_dp_thresh_sq.argtypes = [ctypes.c_void_p, ctypes.c_float]
         L.ofdis_profile_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.ofdis_profile_levels.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -259,6 +261,10 @@ class Context:
     def set_camlr(self, camlr: int):
         self._ck(lib().ofdis_set_camlr(self._h, camlr))
 
+    def set_option(self, name: str, value: int):
+        """Launch-geometry options of ofdis_set_option (results are bit-identical under every setting)."""
+        self._ck(lib().ofdis_set_option(self._h, name.encode(), int(value)))
+
     def set_graph_mode(self, on: bool):
         self._ck(lib().ofdis_set_graph_mode(self._h, 1 if on else 0))
 
@@ -269,6 +275,16 @@ class Context:
         self._ck(lib().ofdis_profile_run(self._h, nframes, steps, ms, n))
         names = ("patch", "densify", "vr_setup", "assemble", "sor")
         return {k: {"ms_per_step": ms[i] / steps, "launches_per_step": n[i] / steps} for i, k in enumerate(names)}
+
+    def profile_levels(self, nframes: int, steps: int = 3):
+        """Like profile_kernels, split by pyramid level: {level: {class: ms_per_step}}."""
+        nlev = self.prm.sc_f - self.prm.sc_l + 1
+        ms = (ctypes.c_double * 5)()
+        n = (ctypes.c_long * 5)()
+        lv = (ctypes.c_double * (5 * nlev))()
+        self._ck(lib().ofdis_profile_levels(self._h, nframes, steps, ms, n, lv))
+        names = ("patch", "densify", "vr_setup", "assemble", "sor")
+        return {self.prm.sc_l + i: {k: lv[i * 5 + j] / steps for j, k in enumerate(names)} for i in range(nlev)}
 
     @property
     def launch_count(self) -> int:
@@ -307,7 +323,10 @@ class OFClass:
         ctx = Context(prm, width, height, imgpadding, 1, device)
         try:
             for lv in range(sc_l, sc_f + 1):
-                ctx.upload_level(0, lv, im_ao[lv], im_ao_dx[lv], im_ao_dy[lv], im_bo[lv])
+                if usefbcon:  # the backward grid's template gradients (oflow.cpp:193-197)
+                    ctx.upload_level_fb(0, lv, im_ao[lv], im_ao_dx[lv], im_ao_dy[lv], im_bo[lv], im_bo_dx[lv], im_bo_dy[lv])
+                else:
+                    ctx.upload_level(0, lv, im_ao[lv], im_ao_dx[lv], im_ao_dy[lv], im_bo[lv])
             if initflow is not None:
                 ctx.set_flow(0, sc_f + 1, initflow)
             ctx.run(1, use_initflow=initflow is not None)

@@ -2,6 +2,7 @@
 // level loop (OFClass::OFClass, oflow.cpp:76-108,138-157,184-295) and transfers.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -15,14 +16,6 @@
 
 using namespace ofdis;
 
-// rows of the skewed SOR arrays: padded to 32/64/128/256 (template sizes of sor_tma_kernel), a
-// multiple of 32 beyond
-static int sor_hpad(int h) {
-  for (int p = 32; p <= 256; p *= 2)
-    if (h <= p) return p;
-  return ((h + 31) / 32) * 32;
-}
-
 struct ofdis_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -33,6 +26,9 @@ struct ofdis_ctx {
   // images); dirs = 2, cap = max_frames * dirs internal frames are allocated
   int dirs = 1, cap = 0;
   int last_vr_fstep = 1;
+  // SOR band plan (sor_band_plan): levels of up to sor_single_max rows run in one CTA, taller ones in a
+  // cluster of up to sor_max_cluster CTAs (8 = portable limit; 16 where the device grants it)
+  int sor_single_max = 128, sor_max_cluster = 8, sor_dev_cluster = 8;
   int nlev = 0;                    // sc_f - sc_l + 1
   std::vector<LevelGeom> lev;      // index: level - sc_l
   std::vector<size_t> img_off;     // [lev][4] offsets (floats) inside one packed frame
@@ -132,6 +128,7 @@ cudaMemcpyKind kind_out(int memkind) { return memkind == OFDIS_MEM_DEVICE ? cuda
 int run_levels(ofdis_ctx* ctx, int nframes, int use_initflow) {
   for (int sl = ctx->prm.sc_f; sl >= ctx->prm.sc_l; --sl) {
     const bool from_coarser = (sl < ctx->prm.sc_f) || use_initflow;
+    if (ctx->prof) ctx->prof->level = sl;
     int rc = ofdis_patgrid_optimize(ctx, sl, 0, nframes, from_coarser ? 1 : 0);
     if (rc) return rc;
     rc = ofdis_patgrid_aggregate(ctx, sl, 0, nframes);
@@ -164,7 +161,10 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
   if (width <= 0 || height <= 0 || (width % (1 << prm->sc_f)) || (height % (1 << prm->sc_f))) return OFDIS_ERR_ARG;
   if (max_frames < 1 || prm->max_iter < 0) return OFDIS_ERR_ARG;
   if (prm->usetvref && ((height >> prm->sc_f) < 4 || (width >> prm->sc_f) < 2)) return OFDIS_ERR_ARG;  // image.c:401-434 needs >= 4 rows
-  if (prm->usetvref && (height >> prm->sc_l) > 1024) return OFDIS_ERR_UNSUPPORTED;  // one SOR thread per row
+  if (prm->usetvref) {  // tallest refinement level: 256-row bands x a cluster of 16 CTAs at most (re-checked for the device below)
+    VarRefPlanes probe{};
+    if (!sor_band_plan(width >> prm->sc_l, height >> prm->sc_l, 128, 16, &probe)) return OFDIS_ERR_UNSUPPORTED;
+  }
 
   ofdis_ctx* ctx = new (std::nothrow) ofdis_ctx();
   if (!ctx) return OFDIS_ERR_NOMEM;
@@ -192,6 +192,17 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
       return OFDIS_ERR_CUDA;
     }
     ctx->own_stream = true;
+  }
+  if (prm->usetvref) {  // tallest refinement level: 256-row bands x the largest cluster the device grants
+    ctx->sor_dev_cluster = sor_max_cluster_size();
+    VarRefPlanes probe{};
+    if (!sor_band_plan(width >> prm->sc_l, height >> prm->sc_l, 128, 8, &probe)) {
+      if (!sor_band_plan(width >> prm->sc_l, height >> prm->sc_l, 128, ctx->sor_dev_cluster, &probe)) {
+        ofdis_destroy(ctx);
+        return OFDIS_ERR_UNSUPPORTED;
+      }
+      ctx->sor_max_cluster = ctx->sor_dev_cluster;
+    }
   }
   ctx->pp.max_iter = prm->max_iter;
   ctx->pp.min_iter = prm->min_iter;
@@ -270,8 +281,15 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
     const LevelGeom& Lf = ctx->lev[0];
     const size_t plane = (size_t)Lf.pitch * Lf.h;
     const int C = prm->noc;
-    // skewed SOR arrays: (W4 + h) diagonals x hpad rows, 8 (rec) + 2 (dudv) float4 per block
-    const size_t diag = (size_t)((Lf.w + 3) / 4 + Lf.h + 2) * sor_hpad(Lf.h);
+    // band-skewed SOR arrays: nb bands x (W4 + hpad + 2) diagonals x hpad rows, 8 (rec) + 2 (dudv)
+    // float4 per block; sized for the largest level under either cluster limit
+    size_t diag = 0;
+    for (const LevelGeom& L : ctx->lev)
+      for (int mc = 8; mc <= ctx->sor_dev_cluster; mc += 8)
+        for (int sm = 32; sm <= 128; sm *= 2) {  // every plan ofdis_set_option can select
+          VarRefPlanes t{};
+          if (sor_band_plan(L.w, L.h, sm, mc, &t)) diag = std::max(diag, (size_t)t.nb * t.ndiag * t.hpad);
+        }
     const size_t per_frame = plane * (1 + C + 8 * C) + diag * 4 * (8 + 2);
     ok = dalloc((void**)&ctx->d_planes, sizeof(float) * per_frame * cap);
     if (ok) {
@@ -561,6 +579,7 @@ int ofdis_patgrid_optimize(ofdis_ctx* ctx, int level, int f0, int f1, int init_f
   if (!ctx) return OFDIS_ERR_ARG;
   LevelGeom* L = level_of(ctx, level);
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_optimize: bad argument");
+  CK(cudaSetDevice(ctx->device));
   const int n = launch_patch_optimize(*L, ctx->pp, f0 * ctx->dirs, f1 * ctx->dirs, init_from_coarser != 0, ctx->stream, ctx->prof);
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "patch_optimize_kernel launch", cudaGetLastError());
   ctx->launches += n;
@@ -571,6 +590,7 @@ int ofdis_patgrid_aggregate(ofdis_ctx* ctx, int level, int f0, int f1) {
   if (!ctx) return OFDIS_ERR_ARG;
   LevelGeom* L = level_of(ctx, level);
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_aggregate: bad argument");
+  CK(cudaSetDevice(ctx->device));
   int n;
   if (ctx->dirs == 2) {
     // both grids' patch positions first; the backward flow is not densified on the last level (oflow.cpp:269-270)
@@ -591,6 +611,7 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   LevelGeom* L = level_of(ctx, level);
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "varref_refine: bad argument");
   if (!ctx->d_planes) return fail(ctx, OFDIS_ERR_ARG, "varref_refine: context created with usetvref=0");
+  CK(cudaSetDevice(ctx->device));
   VarRefParams vp;
   // refine_variational.cpp:36-43
   vp.n_inner = n_inner_override >= 0 ? n_inner_override : ctx->prm.tv_innerit * (level + 1);
@@ -601,9 +622,10 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   vp.half_delta_over3 = ctx->prm.tv_delta * 0.5f / 3.0f;
   VarRefPlanes pl = ctx->planes;
   pl.plane = (size_t)L->pitch * L->h;
-  pl.hpad = sor_hpad(L->h);
+  if (!sor_band_plan(L->w, L->h, ctx->sor_single_max, ctx->sor_max_cluster, &pl))
+    return fail(ctx, OFDIS_ERR_UNSUPPORTED, "varref_refine: level too tall for the largest SOR cluster");
   {
-    const size_t diag = (size_t)((L->w + 3) / 4 + L->h + 2) * pl.hpad;
+    const size_t diag = (size_t)pl.nb * pl.ndiag * pl.hpad;
     pl.rec_stride = diag * (L->nop == 2 ? 8 : 5);
     pl.dudv_stride = diag * 2;
   }
@@ -626,6 +648,26 @@ int ofdis_debug_varref_iters(ofdis_ctx* ctx, int level, int f0, int f1, int n_in
   return varref_impl(ctx, level, f0, f1, n_inner);
 }
 
+int ofdis_set_option(ofdis_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return OFDIS_ERR_ARG;
+  if (!strcmp(name, "sor_single_max")) {
+    if (value != 32 && value != 64 && value != 128) return fail(ctx, OFDIS_ERR_ARG, "sor_single_max: 32, 64 or 128");
+    ctx->sor_single_max = value;
+  } else if (!strcmp(name, "sor_max_cluster")) {
+    if (value != 8 && value != 16) return fail(ctx, OFDIS_ERR_ARG, "sor_max_cluster: 8 or 16");
+    if (value > ctx->sor_dev_cluster) return fail(ctx, OFDIS_ERR_UNSUPPORTED, "sor_max_cluster: the device does not grant clusters of 16 CTAs");
+    VarRefPlanes probe{};
+    if (ctx->prm.usetvref && !sor_band_plan(ctx->lev[0].w, ctx->lev[0].h, 128, value, &probe))
+      return fail(ctx, OFDIS_ERR_UNSUPPORTED, "sor_max_cluster: the finest level needs the larger cluster");
+    ctx->sor_max_cluster = value;
+  } else {
+    return fail(ctx, OFDIS_ERR_ARG, "set_option: unknown option");
+  }
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);  // launch geometry changed
+  ctx->graphs.clear();
+  return OFDIS_OK;
+}
+
 int ofdis_set_graph_mode(ofdis_ctx* ctx, int enabled) {
   if (!ctx) return OFDIS_ERR_ARG;
   ctx->graph_mode = enabled != 0;
@@ -645,8 +687,10 @@ int ofdis_run(ofdis_ctx* ctx, int nframes, int use_initflow) {
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     const int rc = run_levels(ctx, nframes, use_initflow);
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
-    if (rc) return rc;
-    if (e != cudaSuccess) return fail(ctx, OFDIS_ERR_CUDA, "cudaStreamEndCapture", e);
+    if (rc || e != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc ? rc : fail(ctx, OFDIS_ERR_CUDA, "cudaStreamEndCapture", e);
+    }
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
@@ -735,10 +779,11 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
   if (!strcmp(name, "dudv") || !strcmp(name, "rec")) {
     // stored skewed (see VarRefPlanes); returned in natural (h, pitch, per-pixel) order
     const bool is_rec = name[0] == 'r';
-    const int hpad = sor_hpad(L->h), W4 = (L->w + 3) / 4;
+    VarRefPlanes bp{};
+    if (!sor_band_plan(L->w, L->h, ctx->sor_single_max, ctx->sor_max_cluster, &bp)) return OFDIS_ERR_UNSUPPORTED;
     const int nq = is_rec ? (L->nop == 2 ? 8 : 5) : 2;            // float4 (fields) per 4-pixel block
     const int per = is_rec ? (L->nop == 2 ? 8 : 5) : 2;           // floats per pixel
-    const size_t stride = (size_t)(W4 + L->h + 2) * hpad * nq;    // float4 per frame
+    const size_t stride = (size_t)bp.nb * bp.ndiag * bp.hpad * nq;  // float4 per frame
     if (plane * per > max_floats) return OFDIS_ERR_ARG;
     std::vector<float> raw(stride * 4);
     const float4* base = (is_rec ? ctx->planes.rec : ctx->planes.dudv) + (size_t)fr * stride;
@@ -748,7 +793,7 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
       for (int i = 0; i < L->w; ++i)
         for (int e = 0; e < per; ++e) {
           // both are SoA inside the block: float4 e holds field e of the block's 4 pixels
-          const size_t f4 = skew_f4(i >> 2, j, e, nq, hpad);
+          const size_t f4 = band_f4(bp, i >> 2, j, e, nq);
           dst[((size_t)j * L->pitch + i) * per + e] = raw[f4 * 4 + (i & 3)];
         }
     return (long)(plane * per);
@@ -762,6 +807,11 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
 long ofdis_launch_count(const ofdis_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int ofdis_profile_run(ofdis_ctx* ctx, int nframes, int steps, double* ms_by_class, long* launches_by_class) {
+  return ofdis_profile_levels(ctx, nframes, steps, ms_by_class, launches_by_class, nullptr);
+}
+
+int ofdis_profile_levels(ofdis_ctx* ctx, int nframes, int steps, double* ms_by_class, long* launches_by_class,
+                         double* ms_by_level_class) {
   if (!ctx || steps < 1 || !ms_by_class || !launches_by_class) return OFDIS_ERR_ARG;
   if (nframes < 1 || nframes > ctx->max_frames) return fail(ctx, OFDIS_ERR_ARG, "profile_run: bad frame count");
   CK(cudaSetDevice(ctx->device));
@@ -776,11 +826,15 @@ int ofdis_profile_run(ofdis_ctx* ctx, int nframes, int steps, double* ms_by_clas
     ms_by_class[k] = 0.0;
     launches_by_class[k] = 0;
   }
+  if (ms_by_level_class)
+    for (int k = 0; k < ctx->nlev * KC_COUNT; ++k) ms_by_level_class[k] = 0.0;
   for (auto& r : prof.recs) {
     float ms = 0.f;
     if (e == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
       ms_by_class[r.cls] += ms;
       launches_by_class[r.cls] += 1;
+      if (ms_by_level_class && r.level >= ctx->prm.sc_l && r.level <= ctx->prm.sc_f)
+        ms_by_level_class[(r.level - ctx->prm.sc_l) * KC_COUNT + r.cls] += ms;
     }
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);

@@ -49,21 +49,43 @@ struct VarRefPlanes {
   float* mask;             // [frames]
   float* avg;              // [frames][C]   0.5*(I1w+I0)            (setup only)
   float* deriv[8];         // Ix Iy Iz Ixx Ixy Iyy Ixz Iyz, each [frames][C]
-  // Skewed ("anti-diagonal major") storage shared by assemble_kernel and sor_kernel: the 4-pixel
-  // block (row j, columns 4I..4I+3) lives at [d = I + j][q][j] with q the float4 inside the block,
-  // so that the lanes of a SOR warp (consecutive rows, same d at a given super-step) touch
-  // consecutive 16-byte words.  See skew_f4() below.
-  float4* dudv;            // [frames][(W4+h)][2][hpad] float4 = (du,dv) x 2 pixels
-  float4* rec;             // [frames][(W4+h)][4*RF][hpad] float4, RF = 2 (flow) / 1 (stereo)
+  // Band-skewed ("anti-diagonal major") storage shared by assemble_kernel and sor_wave_kernel: the
+  // rows of a level are cut into `nb` bands of `hpad` rows (hpad a power of two; one band per CTA of
+  // the SOR launch).  The 4-pixel block (row j = c*hpad + jl, columns 4I..4I+3) lives at
+  // [band c][d = I + jl][q][jl] with q the float4 inside the block, so that the lanes of a SOR warp
+  // (consecutive rows, same d at a given super-step) touch consecutive 16-byte words and a whole
+  // diagonal of a band is one contiguous bulk copy.  See band_f4() below.
+  float4* dudv;            // [frames][nb][ndiag][2][hpad] float4 = du x4 | dv x4 of a block
+  float4* rec;             // [frames][nb][ndiag][NQ][hpad] float4, NQ = 8 record fields (flow) / 5 (stereo)
   size_t plane;            // pitch*h (natural planes)
   size_t dudv_stride;      // float4 per frame
   size_t rec_stride;       // float4 per frame
-  int hpad;                // rows padded to a multiple of 32
+  int hpad, hshift;        // rows per band, log2
+  int nb;                  // bands
+  int ndiag;               // diagonals stored per band: W4 + hpad + 2
 };
 
-// float4 index of float4 q of block (I, j) in a skewed array with NQ float4 per block
-__host__ __device__ __forceinline__ size_t skew_f4(int I, int j, int q, int NQ, int hpad) {
-  return ((size_t)(I + j) * NQ + q) * hpad + j;
+// float4 index of float4 q of block (I, j) in a band-skewed array with NQ float4 per block
+__host__ __device__ __forceinline__ size_t band_f4(const VarRefPlanes& pl, int I, int j, int q, int NQ) {
+  const int jl = j & (pl.hpad - 1);
+  return (((size_t)(j >> pl.hshift) * pl.ndiag + I + jl) * NQ + q) * pl.hpad + jl;
+}
+
+// Band plan of a level for the SOR (sor_wave_kernel.cuh): levels of up to `single_max` rows run in
+// one CTA (hpad = rows padded to 32/64/128); taller ones are cut into the smallest bands that still
+// fit a cluster of `max_cluster` CTAs.  Returns false when the level is too tall.
+inline bool sor_band_plan(int w, int h, int single_max, int max_cluster, VarRefPlanes* pl) {
+  int hpad = 0;
+  for (int p = 32; p <= 128 && !hpad; p *= 2)
+    if (h <= p && h <= single_max) hpad = p;
+  for (int p = 32; p <= 256 && !hpad; p *= 2)
+    if ((h + p - 1) / p <= max_cluster) hpad = p;
+  if (!hpad) return false;
+  pl->hpad = hpad;
+  pl->hshift = hpad == 32 ? 5 : (hpad == 64 ? 6 : (hpad == 128 ? 7 : 8));
+  pl->nb = (h + hpad - 1) / hpad;
+  pl->ndiag = (w + 3) / 4 + hpad + 2;
+  return true;
 }
 
 struct VarRefParams {
@@ -75,7 +97,8 @@ struct VarRefParams {
 enum KernelClass { KC_PATCH = 0, KC_DENSIFY, KC_VR_SETUP, KC_VR_ASSEMBLE, KC_VR_SOR, KC_COUNT };
 struct Profiler {
   cudaStream_t st = nullptr;
-  struct Rec { int cls; cudaEvent_t a, b; };
+  struct Rec { int cls, level; cudaEvent_t a, b; };
+  int level = 0;  // pyramid level of the launches being recorded
   std::vector<Rec> recs;
   cudaEvent_t cur = nullptr;
   int cur_cls = -1;
@@ -88,7 +111,7 @@ struct Profiler {
     cudaEvent_t b;
     cudaEventCreate(&b);
     cudaEventRecord(b, st);
-    recs.push_back({cur_cls, cur, b});
+    recs.push_back({cur_cls, level, cur, b});
   }
 };
 struct ProfScope {
@@ -118,6 +141,9 @@ int launch_flow_upsample(const LevelGeom& g, int f0, int f1, float* out, int w_o
                          cudaStream_t st);
 int launch_varref(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
                   cudaStream_t st, Profiler* prof = nullptr);
+
+// largest thread-block cluster the SOR kernel can be launched with on the current device (8 or 16)
+int sor_max_cluster_size();
 
 // ---- exact-arithmetic helpers -------------------------------------------------
 // std::min/std::max semantics of the reference (operand order matters for +-0/NaN)

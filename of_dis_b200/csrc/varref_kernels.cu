@@ -8,8 +8,8 @@
 //   assemble_kernel  compute_smoothness + compute_data[_DE] + sub_laplacian (x2) + the 2x2 block
 //                    inversion of sor_coupled's first sweep, fused; smoothness staged through
 //                    shared-memory tiles; writes one 32-byte SOR record per pixel
-//   sor_kernel       all sweeps of the lexicographic SOR as a systolic wavefront
-//                    (one thread per (sweep,row), step t handles column t-row-2*sweep)
+//   sor_wave_kernel  all sweeps of the lexicographic SOR as a systolic wavefront, one CTA or one
+//                    thread-block cluster per frame (sor_wave_kernel.cuh)
 //
 // Every expression keeps the reference's operand order; the TU is compiled with
 // -fmad=false so nothing is contracted (bit-exactness).
@@ -153,10 +153,13 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   const int w = g.w, h = g.h, pitch = g.pitch;
   const float* const flow = g.flow + (size_t)frame * g.flow_frame_stride;
   const float* const dudv = reinterpret_cast<const float*>(pl.dudv + (size_t)fr * pl.dudv_stride);
-  const int hpad = pl.hpad;
-  // float index of du of pixel (x,y) in the skewed layout (skew_f4 with NQ = 2): float4 0 of a
+  const int hpad = pl.hpad, hshift = pl.hshift, ndiag = pl.ndiag;
+  // float index of du of pixel (x,y) in the band-skewed layout (band_f4 with NQ = 2): float4 0 of a
   // block holds du x4, float4 1 (4*hpad floats on) dv x4
-  auto dudv_idx = [hpad](int x, int y) { return ((((x >> 2) + y) * 2) * hpad + y) * 4 + (x & 3); };
+  auto dudv_idx = [hpad, hshift, ndiag](int x, int y) {
+    const int jl = y & (hpad - 1);
+    return ((((y >> hshift) * ndiag + (x >> 2) + jl) * 2) * hpad + jl) * 4 + (x & 3);
+  };
 
   // uu = wx + du (vv likewise); first iteration: uu = wx (refine_variational.cpp:189-190).
   // Coordinates are clamped, which also realises the replicate border of the 3-tap
@@ -349,7 +352,8 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     const float det = iA11 * iA22 - A12 * A12;
     // record of the 4-pixel block, SoA: float4 f of the block holds field f of its 4 pixels;
     // fields: a11^-1, a12^-1, a22^-1, b1, b2, sh, sv, sv(row above)
-    const int b0 = (((i >> 2) + j) * 8 * hpad + j) * 4 + (i & 3);  // skew_f4(I, j, 0, 8, hpad)
+    const int jl = j & (hpad - 1);
+    const int b0 = ((((j >> hshift) * ndiag + (i >> 2) + jl) * 8) * hpad + jl) * 4 + (i & 3);  // band_f4(I, j, 0, 8)
     rec[b0] = iA11 / det;
     rec[b0 + fs] = A12 / -det;
     rec[b0 + 2 * fs] = iA22 / det;
@@ -366,7 +370,8 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     if (j < h - 1) sum += vv;
     if (i < w - 1) sum += hh;
     // stereo record fields: A11 = a11 + sum, b1, sh, sv, sv(row above)
-    const int b0 = (((i >> 2) + j) * 5 * hpad + j) * 4 + (i & 3);  // skew_f4(I, j, 0, 5, hpad)
+    const int jl = j & (hpad - 1);
+    const int b0 = ((((j >> hshift) * ndiag + (i >> 2) + jl) * 5) * hpad + jl) * 4 + (i & 3);  // band_f4(I, j, 0, 5)
     rec[b0] = A11 + sum;
     rec[b0 + fs] = B1;
     rec[b0 + 2 * fs] = hh;
@@ -377,223 +382,17 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
 }
 
 // ---------------------------------------------------------------------------
-// Lexicographic SOR as a systolic wavefront.
-//
-// sor_coupled (solver.c:77-421) visits pixels in raster order; pixel (i,j) of
-// sweep k reads left/top of sweep k and right/bottom (and itself) of sweep k-1.
-// Rows are cut into blocks of 4 columns.  With the schedule
-//      T = I + j + 2k          (I = column block, j = row, k = sweep)
-// every value is produced exactly one super-step before its consumers need it:
-// thread (k,j) walks row j one block per super-step, keeps the left neighbour in
-// registers and exchanges (du,dv,sv) of its block with the threads (k,j+1),
-// (k+1,j) and (k+1,j-1) through a double-buffered shared-memory board; one
-// __syncthreads per super-step, W/4 + h + 2K super-steps in all.  Inside a block
-// the four pixels are updated sequentially with the reference's expression, so
-// the result is bit-identical to the raster scan.  Sweep 0 takes the previous
-// values from global memory (register-prefetched one super-step ahead), the last
-// sweep writes du,dv (and, on the last inner iteration, flow = w + dw; K12).
-// Row-class and border cases are selects, not branches: the loop body is
-// straight-line code.
+// Shared-memory access helpers of the SOR kernel (explicit 128-bit forms).
 __device__ __forceinline__ float4 lds128(unsigned addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-// volatile: one load per call site and per execution -- ptxas otherwise re-materialises
-// ld.global.nc values after the barrier instead of keeping them in registers, which puts an
-// L2 round trip at the head of every super-step
-__device__ __forceinline__ float4 ldg128(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float4 ldg128_rw(const float4* p) {  // data written earlier in this kernel family
-  float4 v;
-  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-#include "sor_tma_kernel.cuh"
-
-// Thread layout: tid = k*hpad + j with hpad a multiple of 32, so the sweep index k (and with
-// it the "sweep 0 reads global / last sweep writes global" roles) is uniform per warp.
-// Out-of-range super-steps execute the same straight-line code on clamped addresses and
-// simply do not store to global memory; whatever they put on the board is never consumed
-// by an in-range neighbour.
-//
-// Register pipeline: two parity sets.  Everything a super-step T needs from global memory
-// (its block's records; for sweep 0 the previous values of its block and of the row below;
-// for the final write the flow) sits in set[T&1], loaded at the end of super-step T-2
-// straight into its final registers (prefetch distance 2, no copies).  The other set holds
-// block I+1, whose first column is the right neighbour of this block's last column.
-struct SorSet {
-  float4 F[8];           // record fields of the block (5 used for stereo)
-  float4 own_u, own_v;   // previous-sweep du / dv of the block
-  float4 bot_u, bot_v;   // sweep 0: previous du / dv of the row below
-};
-
-template <int NOP, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1)
-    sor_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp, int f0, int K, int hpad) {
-  extern __shared__ float4 s_pub[];  // [2][K][h+2][NF]
-  constexpr int NF = (NOP == 2) ? 2 : 1;   // float4 per board entry: du x4, (dv x4)
-  const int fr = blockIdx.x, frame = frame_of(g, f0, fr);
-  const int w = g.w, h = g.h;
-  const int tid = threadIdx.x;
-  // ---- helper warp: the last warp of the CTA only warms L1 -------------------------------------
-  // Sweep 0 is the first toucher of every record / (du,dv) line; an L1-missing warp-level load
-  // takes ~75 cycles to issue against ~17 for a hit, which made the sweep-0 warps 2x slower than
-  // the others and set the pace of every super-step.  One extra warp touches the lines PD
-  // super-steps ahead (one 128-byte line per lane and instruction), so the compute warps only
-  // ever hit L1.
-  if (tid >= K * hpad) {
-    const int lane = tid & 31, W4h = (g.w + 3) >> 2;
-    constexpr int NQh = (NOP == 2) ? 8 : 5, PD = 3;
-    const int S_h = W4h + g.h + 2 * K - 2, dmax_h = W4h + g.h - 1, wps = hpad >> 5;
-    const float4* recb = pl.rec + (size_t)blockIdx.x * pl.rec_stride;
-    const float4* dudb = pl.dudv + (size_t)blockIdx.x * pl.dudv_stride;
-    for (int T = -PD; T < S_h; ++T) {
-      int d = T + PD;   // sweep 0's diagonal of super-step T+PD
-      d = d > dmax_h ? dmax_h : d;
-      // records: NQh rows of hpad float4 -> hpad*NQh/8 lines of 128 bytes
-      for (int ln = lane; ln < wps * 4 * NQh; ln += 32) {
-        float x;
-        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(x) : "l"(recb + (size_t)d * NQh * hpad + ln * 8));
-      }
-      // (du,dv) of diagonal d+1 (own values one step later, row-below values of this step)
-      const int d1 = d + 1 > dmax_h ? dmax_h : d + 1;
-      for (int ln = lane; ln < wps * 4 * 2; ln += 32) {
-        float x;
-        asm volatile("ld.global.f32 %0, [%1];" : "=f"(x) : "l"(dudb + (size_t)d1 * 2 * hpad + ln * 8));
-      }
-      if (T >= 0) __syncthreads();
-    }
-    return;
-  }
-  const int k = tid / hpad, jraw = tid - k * hpad;
-  const bool valid = jraw < h;
-  const int j = valid ? jraw : h - 1;      // idle lanes shadow the last row, never store
-  const int hb = h + 2;
-  const unsigned bufbytes = (unsigned)(K * hb * NF) * 16u;
-  const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_pub);
-  const unsigned a_me = sbase + (unsigned)((k * hb + j + 1) * NF) * 16u;
-  const unsigned a_top = sbase + (unsigned)((k * hb + j) * NF) * 16u;
-  const int km = k > 0 ? k - 1 : 0;
-  const unsigned a_right = sbase + (unsigned)((km * hb + j + 1) * NF) * 16u;
-  const unsigned a_bot = sbase + (unsigned)((km * hb + j + 2) * NF) * 16u;
-  const bool first_row = (j == 0), last_row = (j == h - 1);
-  const bool k0 = (k == 0), klast = (k == K - 1);
-  const float omega = vp.omega;
-
-  // skewed arrays: block (I, j) float4 q at ((I + j) * NQ + q) * hpad + j
-  constexpr int NQ = (NOP == 2) ? 8 : 5;   // record fields (float4) per block
-  const float4* const rec_f = pl.rec + (size_t)fr * pl.rec_stride + j;      // + (d*NQ + q)*hpad
-  float4* const dud_f = pl.dudv + (size_t)fr * pl.dudv_stride + j;         // + (d*2 + q)*hpad
-  const int jbo = (jraw + 1 < hpad) ? 1 : 0;  // lane offset of the row below (stay inside the row of lanes)
-  const int bstep_r = NQ * hpad, bstep_d = 2 * hpad;  // float4 per diagonal
-  (void)frame;
-
-  const int W4 = (w + 3) >> 2;
-  const int tstart = j + 2 * k;
-  const int S = W4 + h + 2 * K - 2;  // super-steps 0 .. (W4-1)+(h-1)+2(K-1)
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  // Loads the block this thread handles at super-step `Tn` into a parity set.  Addresses are
-  // formed from the DIAGONAL d = I + j = Tn - 2k, which is the same for all lanes of a warp, so
-  // every load instruction touches 512 contiguous bytes even when some lanes are out of range
-  // (clamping the block index per lane instead scatters those lanes over up to 32 lines per
-  // instruction and cost ~1200 cycles per super-step on sweep 0).  d is clamped uniformly; lanes
-  // whose block does not exist read garbage they never use.
-  const int dmax = W4 + h - 1;
-  auto load_set = [&](SorSet& s, int Tn) {
-    int d = Tn - 2 * k;
-    d = d < 0 ? 0 : (d > dmax ? dmax : d);
-    const float4* rp = rec_f + (size_t)d * bstep_r;
-#pragma unroll
-    for (int f = 0; f < NQ; ++f) s.F[f] = ldg128(rp + f * hpad);
-    if (k0) {
-      const int d1 = d + 1 > dmax ? dmax : d + 1;   // row below: diagonal d+1, lane j+1
-      s.own_u = ldg128_rw(dud_f + (size_t)d * bstep_d);
-      s.bot_u = ldg128_rw(dud_f + (size_t)d1 * bstep_d + jbo);
-      if (NOP == 2) {
-        s.own_v = ldg128_rw(dud_f + (size_t)d * bstep_d + hpad);
-        s.bot_v = ldg128_rw(dud_f + (size_t)d1 * bstep_d + hpad + jbo);
-      }
-    }
-  };
-
-  float du_l = 0.f, dv_l = 0.f, hl = 0.f;
-  unsigned prevb = bufbytes, curb = 0;   // T even: write buffer 0, read buffer 1
-
-  // one super-step: `cur` holds block I, `nxt` block I+1
-  // Rows of this warp.  A warp none of whose rows is within 3 super-steps of holding a block (the
-  // register sets are filled two steps ahead, the previous-sweep hand-over one step ahead) skips
-  // the body: on a 1440x1024 level only ~12 of the 32 warps are inside the wavefront at a time.
-  // Warps made of shadow lanes only (rows >= h) never run it: a shadow lane that joined late would
-  // carry a wrong left-neighbour state into the board slot it shares with the real last row.
-  const int jw_lo = jraw & ~31, jw_hi = (jw_lo + 31 < h - 1) ? jw_lo + 31 : h - 1;
-  auto step = [&](SorSet& cur, SorSet& nxt, int I, int T) {
-    const bool in_range = valid & (I >= 0) & (I < W4);
-    SOR_STAMP(0, omega, omega);
-    const int n = T - 2 * k;
-    if (jw_lo < h && jw_lo <= n + 3 && jw_hi > n - W4) {
-    if (!k0) {  // previous-sweep values come from the board (written one super-step ago)
-      nxt.own_u = lds128(a_right + prevb);
-      cur.bot_u = lds128(a_bot + prevb);
-      if (NOP == 2) {
-        nxt.own_v = lds128(a_right + prevb + 16);
-        cur.bot_v = lds128(a_bot + prevb + 16);
-      }
-    }
-    const float4 top_u = lds128(a_top + prevb);
-    const float4 top_v = (NOP == 2) ? lds128(a_top + prevb + 16) : z4;
-    float nu[4], nv[4];
-    const int col0 = 4 * I;
-    {
-      // the block's records are needed no further once copied: refill the set for super-step
-      // T+2 now, so the loads fly while the recurrence keeps the pipeline latency-bound anyway
-      float4 Fc[NQ];
-#pragma unroll
-      for (int f = 0; f < NQ; ++f) Fc[f] = cur.F[f];
-      const float4 ownu = cur.own_u, ownv = cur.own_v, botu = cur.bot_u, botv = cur.bot_v;
-      load_set(cur, T + 2);
-      sor_block_update<NOP>(Fc, ownu, ownv, nxt.own_u.x, nxt.own_v.x, top_u, top_v, botu, botv, first_row, last_row,
-                            col0, w, omega, du_l, dv_l, hl, nu, nv);
-    }
-    sts128(a_me + curb, make_float4(nu[0], nu[1], nu[2], nu[3]));
-    if (NOP == 2) sts128(a_me + curb + 16, make_float4(nv[0], nv[1], nv[2], nv[3]));
-    if (klast && in_range) {
-      float4* dst = dud_f + (size_t)(I + j) * bstep_d;
-      dst[0] = make_float4(nu[0], nu[1], nu[2], nu[3]);
-      if (NOP == 2) dst[hpad] = make_float4(nv[0], nv[1], nv[2], nv[3]);
-    }
-    }
-    SOR_STAMP(5, omega, omega);
-    __syncthreads();
-    SOR_STAMP(6, omega, omega);
-    const unsigned tmp = prevb;
-    prevb = curb;
-    curb = tmp;
-  };
-
-  SorSet s0, s1;
-  s0.own_u = s0.own_v = s0.bot_u = s0.bot_v = z4;
-  s1.own_u = s1.own_v = s1.bot_u = s1.bot_v = z4;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-  }
-  load_set(s0, 0);   // super-step 0
-  load_set(s1, 1);   // super-step 1
-  int I = -tstart;
-#pragma unroll 1
-  for (int T = 0; T < S; T += 2, I += 2) {
-    step(s0, s1, I, T);
-    if (T + 1 < S) step(s1, s0, I + 1, T + 1);
-  }
-}
+#include "sor_wave_kernel.cuh"
 
 // K12 at the end of the level: flow = w + dw (refine_variational.cpp:210-221; stereo clamp
 // :299-314).  Kept out of the SOR kernel: the flow array is row-major per frame, so reading it
@@ -604,7 +403,7 @@ __global__ void __launch_bounds__(256) flow_update_kernel(LevelGeom g, VarRefPla
   const int fr = blockIdx.z, frame = frame_of(g, f0, fr);
   if (i >= g.w || j >= g.h) return;
   const float* dudv = reinterpret_cast<const float*>(pl.dudv + (size_t)fr * pl.dudv_stride);
-  const size_t b = skew_f4(i >> 2, j, 0, 2, pl.hpad) * 4 + (i & 3);
+  const size_t b = band_f4(pl, i >> 2, j, 0, 2) * 4 + (i & 3);
   float* f = g.flow + (size_t)frame * g.flow_frame_stride + ((size_t)j * g.w + i) * NOP;
   if (NOP == 2) {
     const float2 wv = *reinterpret_cast<const float2*>(f);
@@ -616,6 +415,59 @@ __global__ void __launch_bounds__(256) flow_update_kernel(LevelGeom g, VarRefPla
 }
 
 }  // namespace
+
+// Largest number of sweeps one launch can keep in flight: K*hpad compute threads + the producer
+// warp within the kernel's launch bound, stage ring + board within the 227 KB of an SM.
+static int sor_sweeps_per_launch(int nop, int hpad, int K) {
+  int kl = K < 1 ? 1 : K;
+  while (kl > 1 && (kl * hpad + 32 > sor_max_threads(hpad) || sor_smem_bytes(nop, hpad, kl) > 227 * 1024)) --kl;
+  return kl;
+}
+
+template <int NOP, int HPAD, bool CL>
+static cudaError_t launch_sor_t(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int nf, int kl,
+                                cudaStream_t st) {
+  auto kern = sor_wave_kernel<NOP, HPAD, CL>;
+  const size_t smem = sor_smem_bytes(NOP, HPAD, kl);
+  // opt-in shared memory (and cluster size) once per device and instantiation
+  static size_t smem_set[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && smem_set[dev] < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && CL) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    smem_set[dev] = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(nf * (CL ? pl.nb : 1)));
+  cfg.blockDim = dim3((unsigned)(kl * HPAD + 32));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (CL) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)pl.nb;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, g, pl, vp, kl);
+}
+
+template <int NOP>
+static cudaError_t launch_sor(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int nf, int kl,
+                              cudaStream_t st) {
+  const bool cl = pl.nb > 1;
+  switch (pl.hpad) {
+    case 32: return cl ? launch_sor_t<NOP, 32, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 32, false>(g, pl, vp, nf, kl, st);
+    case 64: return cl ? launch_sor_t<NOP, 64, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 64, false>(g, pl, vp, nf, kl, st);
+    case 128: return cl ? launch_sor_t<NOP, 128, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 128, false>(g, pl, vp, nf, kl, st);
+    case 256: return cl ? launch_sor_t<NOP, 256, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 256, false>(g, pl, vp, nf, kl, st);
+  }
+  return cudaErrorInvalidValue;
+}
 
 template <int C, int NOP>
 static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
@@ -637,48 +489,11 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
     cudaMemsetAsync(pl.dudv, 0, sizeof(float4) * pl.dudv_stride * nf, st);
   }
   launches += 3;
-  // sweeps per SOR launch: all of them when (sweeps x padded rows) fits a 512-thread CTA (128
-  // registers per thread); otherwise one sweep per launch, 1024-thread variant for tall levels.
+  // SOR: band plan of the level (pl.hpad rows per band, pl.nb bands == CTAs of a cluster) and as
+  // many sweeps per launch as the CTA's thread and shared-memory budgets hold (sweeps are sequential,
+  // so K sweeps in ceil(K / kl) launches give the same result)
   const int K = vp.n_solver;
-  const int hpad = pl.hpad;  // rows padded to 32/64/128/256 (or a multiple of 32 beyond)
-  const bool fused = (K >= 1) && (K * hpad + 32 <= 512);
-  const int kl = fused ? K : 1;
-  // + one helper (L1 prefetch) warp unless that would exceed the 1024-thread CTA limit
-  const int nthreads = (kl * hpad + 32 <= 1024) ? kl * hpad + 32 : kl * hpad;
-  const int nf4 = (NOP == 2) ? 2 : 1;
-  const size_t smem = sizeof(float4) * 2 * kl * (g.h + 2) * nf4;
-  // register budget follows the CTA size: <=256 threads -> up to 255 registers (no reuse of
-  // in-flight load destinations), <=512 -> 128, else 64 (spills; only for very tall levels)
-  const int variant = nthreads <= 256 ? 0 : (nthreads <= 512 ? 1 : 2);
-  if (K >= 1) {
-    if (variant == 0) cudaFuncSetAttribute(sor_kernel<NOP, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else if (variant == 1) cudaFuncSetAttribute(sor_kernel<NOP, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else cudaFuncSetAttribute(sor_kernel<NOP, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  }
-  // TMA-producer variant when all sweeps fit one CTA (<= 288 threads; 448 when rows are padded to
-  // 128) and the stage ring fits shared memory: level heights up to 128 rows with 3 sweeps
-  const int tma_threads = K * hpad + 32;
-  const size_t tma_smem = (size_t)sor_tma_stages(K) * ((NOP == 2 ? 8 : 5) + 2) * hpad * 16 +
-                          sizeof(float4) * 2 * (size_t)K * (g.h + 2) * nf4 + 8 * (size_t)sor_tma_stages(K);
-  // tuning knob of tools/lanes_probe.py: a larger request limits how many SOR CTAs share an SM
-  static const long exp_min_smem = getenv("OFDIS_EXP_SOR_SMEM_KB") ? atol(getenv("OFDIS_EXP_SOR_SMEM_KB")) * 1024 : 0;
-  const size_t tma_smem_req = tma_smem < (size_t)exp_min_smem ? (size_t)exp_min_smem : tma_smem;
-  // thread budget: 288 (<= 3 sweeps x 64 rows, 2 x 128, 1 x 256) or, for rows padded to 128, 448
-  static const bool exp_no_tma128 = getenv("OFDIS_EXP_NO_TMA128") != nullptr;  // A/B knob of tools/hd_probe.py (1920x1080: 1.32 -> 0.63 ms per 16 pairs)
-  const bool use_tma = (K >= 1) && tma_threads <= ((hpad == 128 && !exp_no_tma128) ? 448 : 288) && tma_smem <= 220 * 1024 &&
-                       (hpad == 32 || hpad == 64 || hpad == 128 || hpad == 256);
-  auto launch_tma = [&]() {
-#define SOR_TMA_LAUNCH(HP)                                                                             \
-  do {                                                                                                 \
-    cudaFuncSetAttribute(sor_tma_kernel<NOP, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_req); \
-    sor_tma_kernel<NOP, HP><<<nf, tma_threads, tma_smem_req, st>>>(g, pl, vp, K);                            \
-  } while (0)
-    if (hpad == 32) SOR_TMA_LAUNCH(32);
-    else if (hpad == 64) SOR_TMA_LAUNCH(64);
-    else if (hpad == 128) SOR_TMA_LAUNCH(128);
-    else SOR_TMA_LAUNCH(256);
-#undef SOR_TMA_LAUNCH
-  };
+  const int kl = sor_sweeps_per_launch(NOP, pl.hpad, K);
   for (int it = 0; it < vp.n_inner; ++it) {
     {
       ProfScope scope(prof, KC_VR_ASSEMBLE);
@@ -687,18 +502,9 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
       else assemble_kernel<C, NOP, 1><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
     }
     ++launches;
-    if (use_tma) {
+    for (int s = 0; s < K; s += kl) {
       ProfScope scope(prof, KC_VR_SOR);
-      launch_tma();
-      ++launches;
-      continue;
-    }
-    const int nl = fused ? 1 : K;
-    for (int s = 0; s < nl; ++s) {
-      ProfScope scope(prof, KC_VR_SOR);
-      if (variant == 0) sor_kernel<NOP, 256><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad);
-      else if (variant == 1) sor_kernel<NOP, 512><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad);
-      else sor_kernel<NOP, 1024><<<nf, nthreads, smem, st>>>(g, pl, vp, f0, kl, hpad);
+      if (launch_sor<NOP>(g, pl, vp, nf, (K - s < kl) ? K - s : kl, st) != cudaSuccess) return -1;
       ++launches;
     }
   }
@@ -715,6 +521,37 @@ extern "C" int ofdis_debug_sor_times(long long* dst) {
   return cudaMemcpyFromSymbol(dst, g_sor_times, sizeof(g_sor_times)) == cudaSuccess ? 0 : -1;
 }
 #endif
+
+int sor_max_cluster_size() {
+  // 16 CTAs is a non-portable cluster size: ask the occupancy calculator whether one such cluster
+  // of the largest SOR configuration (256-row bands, one sweep) fits this device
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 8;
+  if (cached[dev]) return cached[dev];
+  int best = 8;
+  auto kern = sor_wave_kernel<2, 256, true>;
+  const size_t smem = sor_smem_bytes(2, 256, 1);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16);
+    cfg.blockDim = dim3(288);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n >= 1) best = 16;
+  }
+  cudaGetLastError();  // a refused query must not poison later launches
+  cached[dev] = best;
+  return best;
+}
 
 int launch_varref(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
                   cudaStream_t st, Profiler* prof) {

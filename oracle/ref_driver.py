@@ -108,3 +108,40 @@ def ref_level_varref(pyr, prm, level: int, flow: np.ndarray) -> np.ndarray:
         ctypes.c_int(pyr.width), ctypes.c_int(pyr.height), ctypes.c_int(level),
         ctypes.c_int(pyr.imgpadding), ctypes.byref(cp), _fp(out))
     return out
+
+
+def ref_run_many(pyrs, prm, nrep: int = 1, threads: int = 1):
+    """OFClass ctor over `pyrs` x nrep on a native std::thread pool (no Python inside the timed
+    region).  Returns (wall seconds, flows [(h, w, nop)] of the last pass)."""
+    lib = _lib(prm.flavour())
+    h, w = pyrs[0].level_shape(prm.sc_l)
+    out = np.zeros((len(pyrs), h, w, prm.nop), dtype=np.float32)
+    cp = prm.to_c()
+    PP = ctypes.POINTER(_FP)
+    tables = []  # keep the per-pair pointer tables alive
+    ptrs = (PP * (6 * len(pyrs)))()
+    for q, pyr in enumerate(pyrs):
+        for k, x in enumerate((pyr.i0, pyr.i0x, pyr.i0y, pyr.i1, pyr.i1x, pyr.i1y)):
+            t = _pyr_ptrs(x)
+            tables.append(t)
+            ptrs[q * 6 + k] = ctypes.cast(t, PP)
+    lib.ofdis_ref_run_many.restype = ctypes.c_double
+    sec = lib.ofdis_ref_run_many(ptrs, ctypes.c_int(len(pyrs)), ctypes.c_int(nrep), ctypes.c_int(threads),
+                                 ctypes.c_int(pyrs[0].imgpadding), _fp(out), ctypes.c_size_t(h * w * prm.nop),
+                                 ctypes.c_int(pyrs[0].width), ctypes.c_int(pyrs[0].height), ctypes.byref(cp))
+    return float(sec), out
+
+
+def ref_run_many_u8(frames: np.ndarray, prm, nrep: int = 1, threads: int = 1):
+    """8-bit frames [pair][2][h][w][noc] -> full-resolution flow [pair][h][w][nop]: pyramid construction,
+    OFClass and the final upsampling/crop per pair on a native thread pool (what one run_OF_INT call
+    computes between imread and SaveFlowFile).  Returns (wall seconds, flows)."""
+    lib = _lib(prm.flavour())
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    n, _, h, w = frames.shape[:4]
+    out = np.zeros((n, h, w, prm.nop), dtype=np.float32)
+    cp = prm.to_c()
+    lib.ofdis_ref_run_many_u8.restype = ctypes.c_double
+    sec = lib.ofdis_ref_run_many_u8(frames.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n), ctypes.c_int(nrep),
+                                    ctypes.c_int(threads), ctypes.c_int(w), ctypes.c_int(h), _fp(out), ctypes.byref(cp))
+    return float(sec), out

@@ -8,6 +8,10 @@
 //   ofdis_ref_run            -> OFC::OFClass ctor            (oflow.cpp:32-363)
 //   ofdis_ref_level_patches  -> PatGridClass one level       (patchgrid.cpp:98-397)
 //   ofdis_ref_level_varref   -> VarRefClass one level        (refine_variational.cpp:25-116)
+//   ofdis_ref_run_many       -> OFClass ctor over many pairs on a std::thread pool (frame-parallel CPU
+//                               baseline without any Python in the timed region)
+//   ofdis_ref_run_many_u8    -> the same from 8-bit frames to full-resolution flow: the callers either side
+//                               of OFClass (run_dense.cpp:130-178,298-311,407-421) restated without OpenCV
 //
 // One shared object is built per (SELECTMODE, SELECTCHANNEL) pair because the
 // reference selects flow/stereo and gray/RGB at compile time (CMakeLists.txt:25-46).
@@ -18,6 +22,8 @@
 #include <cstring>
 #include <algorithm>
 #include <sys/time.h>
+#include <atomic>
+#include <thread>
 
 #include <Eigen/Core>
 
@@ -164,6 +170,174 @@ void ofdis_ref_time_run(const float** i0, const float** i0x, const float** i0y, 
     gettimeofday(&b, nullptr);
     ms_out[r] = (b.tv_sec - a.tv_sec) * 1000.0 + (b.tv_usec - a.tv_usec) / 1000.0;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Frame-parallel drivers for the CPU baseline.  OFClass instances share no mutable state, so the
+// only way the (single-threaded) reference uses a many-core host is one pair per thread.
+
+// `npairs` pairs, pair q = pointer tables [6][nlevels] at ptrs[q*6 + {0:i0,1:i0x,2:i0y,3:i1,4:i1x,5:i1y}];
+// `nrep` passes over all pairs on `threads` workers; returns wall seconds of the whole job.
+double ofdis_ref_run_many(const float*** ptrs, int npairs, int nrep, int threads, int imgpadding, float* outflow,
+                          size_t outflow_stride, int width, int height, const ofdis_ref_params* p) {
+  std::atomic<long> next(0);
+  const long total = (long)npairs * nrep;
+  struct timeval a, b;
+  gettimeofday(&a, nullptr);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&]() {
+      for (long i = next.fetch_add(1); i < total; i = next.fetch_add(1)) {
+        const int q = (int)(i % npairs);
+        const float*** pp = ptrs + (size_t)q * 6;
+        ofdis_ref_run(pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], imgpadding, outflow + (size_t)q * outflow_stride, nullptr,
+                      width, height, p);
+      }
+    });
+  for (auto& th : pool) th.join();
+  gettimeofday(&b, nullptr);
+  return (b.tv_sec - a.tv_sec) + (b.tv_usec - a.tv_usec) * 1e-6;
+}
+
+namespace {
+// Callers either side of OFClass in run_dense.cpp, restated without OpenCV (the image holds no
+// OpenCV SDK).  For 8-bit input these reproduce cv::resize(0.5, INTER_AREA-equivalent 2x2 mean of the
+// reference's INTER_LINEAR at exact half size), cv::Sobel(3x3)/8 with BORDER_REFLECT_101, copyMakeBorder
+// and the final cv::resize(INTER_LINEAR) exactly (tests/test_preprocess.py pins the same arithmetic
+// of of_dis_b200/preprocess.py to cv2).
+struct Img {
+  int w = 0, h = 0, c = 1;
+  std::vector<float> px;
+  float& at(int x, int y, int k) { return px[((size_t)y * w + x) * c + k]; }
+  float at(int x, int y, int k) const { return px[((size_t)y * w + x) * c + k]; }
+};
+inline int clampi(int v, int n) { return v < 0 ? 0 : (v > n - 1 ? n - 1 : v); }
+inline int refl(int v, int n) {
+  if (n == 1) return 0;
+  while (v < 0 || v >= n) v = v < 0 ? -v : 2 * (n - 1) - v;
+  return v;
+}
+Img border(const Img& s, int pad, bool replicate) {  // copyMakeBorder (run_dense.cpp:163-172)
+  Img d;
+  d.w = s.w + 2 * pad; d.h = s.h + 2 * pad; d.c = s.c;
+  d.px.assign((size_t)d.w * d.h * d.c, 0.f);
+  for (int y = 0; y < d.h; ++y)
+    for (int x = 0; x < d.w; ++x) {
+      const int sx = x - pad, sy = y - pad;
+      if (!replicate && (sx < 0 || sy < 0 || sx >= s.w || sy >= s.h)) continue;
+      for (int k = 0; k < s.c; ++k) d.at(x, y, k) = s.at(clampi(sx, s.w), clampi(sy, s.h), k);
+    }
+  return d;
+}
+Img half(const Img& s) {  // cv::resize(.5,.5) on even sizes (run_dense.cpp:150)
+  Img d;
+  d.w = s.w / 2; d.h = s.h / 2; d.c = s.c;
+  d.px.resize((size_t)d.w * d.h * d.c);
+  for (int y = 0; y < d.h; ++y)
+    for (int x = 0; x < d.w; ++x)
+      for (int k = 0; k < s.c; ++k)
+        d.at(x, y, k) = ((s.at(2 * x, 2 * y, k) + s.at(2 * x + 1, 2 * y, k)) + (s.at(2 * x, 2 * y + 1, k) + s.at(2 * x + 1, 2 * y + 1, k))) * 0.25f;
+  return d;
+}
+void sobel(const Img& s, Img& dx, Img& dy) {  // cv::Sobel 3x3, scale 1/8 (run_dense.cpp:156-157)
+  dx = s; dy = s;
+  for (int y = 0; y < s.h; ++y)
+    for (int x = 0; x < s.w; ++x)
+      for (int k = 0; k < s.c; ++k) {
+        const int xm = refl(x - 1, s.w), xp = refl(x + 1, s.w), ym = refl(y - 1, s.h), yp = refl(y + 1, s.h);
+        const float t0 = s.at(xp, ym, k) - s.at(xm, ym, k), t1 = s.at(xp, y, k) - s.at(xm, y, k), t2 = s.at(xp, yp, k) - s.at(xm, yp, k);
+        dx.at(x, y, k) = (t0 * 0.125f + t1 * 0.25f) + t2 * 0.125f;
+        const float s0 = (s.at(xm, ym, k) * 0.125f + s.at(x, ym, k) * 0.25f) + s.at(xp, ym, k) * 0.125f;
+        const float s2 = (s.at(xm, yp, k) * 0.125f + s.at(x, yp, k) * 0.25f) + s.at(xp, yp, k) * 0.125f;
+        dy.at(x, y, k) = s2 - s0;
+      }
+}
+struct Pyr {
+  std::vector<Img> im, dx, dy;
+  std::vector<const float*> pim, pdx, pdy;
+  void build(const unsigned char* u8, int w_org, int h_org, int c, int W, int H, int lv_f, int pad) {
+    // divisibility padding: replicate, floor(pad/2) left/top (run_dense.cpp:298-311), then float
+    Img base;
+    base.w = W; base.h = H; base.c = c;
+    base.px.resize((size_t)W * H * c);
+    const int pl = (W - w_org) / 2, pt = (H - h_org) / 2;
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x)
+        for (int k = 0; k < c; ++k)
+          base.at(x, y, k) = (float)u8[((size_t)clampi(y - pt, h_org) * w_org + clampi(x - pl, w_org)) * c + k];
+    im.resize(lv_f + 1); dx.resize(lv_f + 1); dy.resize(lv_f + 1);
+    pim.resize(lv_f + 1); pdx.resize(lv_f + 1); pdy.resize(lv_f + 1);
+    for (int i = 0; i <= lv_f; ++i) {
+      im[i] = i == 0 ? base : half(im[i - 1]);
+      sobel(im[i], dx[i], dy[i]);
+    }
+    for (int i = 0; i <= lv_f; ++i) {
+      im[i] = border(im[i], pad, true);
+      dx[i] = border(dx[i], pad, false);
+      dy[i] = border(dy[i], pad, false);
+      pim[i] = im[i].px.data(); pdx[i] = dx[i].px.data(); pdy[i] = dy[i].px.data();
+    }
+  }
+};
+// flow of level sc_l -> x 2^sc_l, cv::resize(INTER_LINEAR) by 2^sc_l, crop (run_dense.cpp:407-414)
+void upsample_crop(const float* fl, int w, int h, int nop, int sc, int w_org, int h_org, int W, int H, float* out) {
+  const float scale = (float)sc;
+  const int cx = (W - w_org) / 2, cy = (H - h_org) / 2;
+  std::vector<int> x0(W), x1(W), y0(H), y1(H);
+  std::vector<float> fx(W), fy(H);
+  auto taps = [&](int ns, int nd, std::vector<int>& a, std::vector<int>& b, std::vector<float>& f) {
+    for (int x = 0; x < nd; ++x) {
+      const float t = ((float)x + 0.5f) / scale - 0.5f;
+      const int i = (int)floorf(t);
+      f[x] = i < 0 ? 0.f : t - (float)i;
+      a[x] = clampi(i, ns);
+      b[x] = clampi(i + 1, ns);
+    }
+  };
+  taps(w, W, x0, x1, fx);
+  taps(h, H, y0, y1, fy);
+  for (int y = 0; y < h_org; ++y)
+    for (int x = 0; x < w_org; ++x) {
+      const int X = x + cx, Y = y + cy;
+      for (int k = 0; k < nop; ++k) {
+        auto S = [&](int xx, int yy) { return fl[((size_t)yy * w + xx) * nop + k] * scale; };
+        const float r0 = S(x0[X], y0[Y]) * (1.0f - fx[X]) + S(x1[X], y0[Y]) * fx[X];
+        const float r1 = S(x0[X], y1[Y]) * (1.0f - fx[X]) + S(x1[X], y1[Y]) * fx[X];
+        out[((size_t)y * w_org + x) * nop + k] = r0 * (1.0f - fy[Y]) + r1 * fy[Y];
+      }
+    }
+}
+}  // namespace
+
+// 8-bit frames [pair][2][h_org][w_org][noc] in, full-resolution flow [pair][h_org][w_org][nop] out: what
+// one run_OF_INT invocation computes between imread and SaveFlowFile.  Returns wall seconds.
+double ofdis_ref_run_many_u8(const unsigned char* frames, int npairs, int nrep, int threads, int w_org, int h_org,
+                             float* out, const ofdis_ref_params* p) {
+  const int nop = (SELECTMODE == 1) ? 2 : 1, c = p->noc, scf = 1 << p->sc_f;
+  const int W = (w_org + scf - 1) / scf * scf, H = (h_org + scf - 1) / scf * scf;
+  const size_t img = (size_t)w_org * h_org * c;
+  std::atomic<long> next(0);
+  const long total = (long)npairs * nrep;
+  struct timeval a, b;
+  gettimeofday(&a, nullptr);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&]() {
+      for (long i = next.fetch_add(1); i < total; i = next.fetch_add(1)) {
+        const int q = (int)(i % npairs);
+        Pyr A, B;
+        A.build(frames + (size_t)q * 2 * img, w_org, h_org, c, W, H, p->sc_f, p->p_samp_s);
+        B.build(frames + (size_t)q * 2 * img + img, w_org, h_org, c, W, H, p->sc_f, p->p_samp_s);
+        const int w = W >> p->sc_l, h = H >> p->sc_l;
+        std::vector<float> fl((size_t)w * h * nop);
+        ofdis_ref_run(A.pim.data(), A.pdx.data(), A.pdy.data(), B.pim.data(), B.pdx.data(), B.pdy.data(), p->p_samp_s,
+                      fl.data(), nullptr, W, H, p);
+        upsample_crop(fl.data(), w, h, nop, 1 << p->sc_l, w_org, h_org, W, H, out + (size_t)q * w_org * h_org * nop);
+      }
+    });
+  for (auto& th : pool) th.join();
+  gettimeofday(&b, nullptr);
+  return (b.tv_sec - a.tv_sec) + (b.tv_usec - a.tv_usec) * 1e-6;
 }
 
 }  // extern "C"

@@ -204,9 +204,9 @@ def test_properties_at_full_size(api):
     assert epe < 0.5, epe
 
 
-def test_tall_level_1024_rows_uses_the_one_thread_per_row_limit(api, oracle_port):
-    """Refinement level with exactly 1024 rows (the SOR kernel's one-thread-per-row ceiling, as in
-    BASELINE configs[4]'s level 1): narrow stereo pair so the oracle stays fast."""
+def test_tall_level_1024_rows_runs_as_a_cluster_of_eight_bands(api, oracle_port):
+    """Refinement level with exactly 1024 rows (as in BASELINE configs[4]'s level 1; 8 bands of 128 rows,
+    one CTA of a thread-block cluster each): narrow stereo pair so the oracle stays fast."""
     prm = params.from_cli_numbers("2 1 8 8 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split(), noc=1, nop=1)
     i0, i1, _ = synth.synthetic_pair(2048, 96, 1, seed=9, amp=3.0, stereo=True)
     pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
@@ -215,8 +215,77 @@ def test_tall_level_1024_rows_uses_the_one_thread_per_row_limit(api, oracle_port
     ctx.run(1)
     assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "run h=1024")
     ctx.close()
-    with pytest.raises(api.OfdisError):  # one row more is rejected, not mis-computed
-        api.Context(prm, 96, 2112, 8, 1)
+
+
+@pytest.mark.parametrize("nop,rows,sweeps", [(2, 1100, 3), (1, 2048, 2)])
+def test_levels_taller_than_1024_rows(nop, rows, sweeps, api, oracle_port):
+    """Levels beyond 8 x 128 rows: bands of 256 rows, one sweep per launch (the round-1 kernel refused these).
+    1100 rows = 5 bands (the last one 76 rows), 2048 rows = the full cluster of 8."""
+    prm = params.from_cli_numbers(("1 0 6 6 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 %d 1.6 0" % sweeps).split(), noc=1, nop=nop)
+    i0, i1, _ = synth.synthetic_pair(rows, 72, 1, seed=11, amp=2.0, stereo=(nop == 1))
+    pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
+    ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    ctx.upload_pyramids(0, pyr)
+    ctx.run(1)
+    assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "run h=%d" % rows)
+    ctx.close()
+
+
+CLUSTER_CASES = ["cfg2_1024x436_gray_op2", "rgb_op3_l1cost_small", "stereo_op4_small", "gray_p6_nopatnorm_sor5",
+                 "gray_sor2_rows70", "stereo_sor1_rows100"]
+
+
+@pytest.mark.parametrize("single_max", [32, 64])
+@pytest.mark.parametrize("name", CLUSTER_CASES)
+def test_cluster_sor_on_small_levels_vs_oracle(name, single_max, api, oracle_port):
+    """ofdis_set_option("sor_single_max"): the same levels solved by a cluster of 32- or 64-row bands instead of
+    one CTA (2..5 bands, partial last bands, 1..5 sweeps, flow and stereo) -- dudv after two inner iterations and
+    the whole run, bitwise; two frames per launch so that consecutive clusters share the grid."""
+    h, w, ch, mk, amp, stereo = CASES[name]
+    prm = mk()
+    pyrs = []
+    for s in range(2):
+        i0, i1, _ = synth.synthetic_pair(h, w, ch, seed=1 + s, amp=amp, stereo=stereo)
+        pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
+    ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, 2)
+    ctx.set_option("sor_single_max", single_max)
+    for f, p in enumerate(pyrs):
+        ctx.upload_pyramids(f, p)
+    lv = prm.sc_l
+    hh, ww = pyrs[0].level_shape(lv)
+    rng = np.random.default_rng(3)
+    dense = (rng.standard_normal((hh, ww, prm.nop)) * 1.5).astype(np.float32)
+    if stereo:
+        dense = -np.abs(dense)
+    st = oracle_port.varref_stages(pyrs[1], prm, lv, dense, n_iters=2)
+    ctx.set_flow(1, lv, dense)
+    ctx.varref_refine(lv, 0, 2, n_inner=2)
+    dudv = ctx.debug_get("dudv", 1, lv)
+    assert_bits(dudv[..., 0], st["iters"][1]["du"], "du")
+    if prm.nop == 2:
+        assert_bits(dudv[..., 1], st["iters"][1]["dv"], "dv")
+    ctx.set_graph_mode(True)
+    ctx.run(2)
+    for f, p in enumerate(pyrs):
+        assert_bits(ctx.get_flow(f, prm.sc_l), oracle_port.port_run(p, prm), "run, frame %d" % f)
+    ctx.close()
+
+
+def test_cluster_of_sixteen_bands_where_the_device_grants_it(api, oracle_port):
+    """Non-portable cluster size 16: 1100-row level as 9 bands of 128 rows (all sweeps in flight)."""
+    prm = params.from_cli_numbers("1 0 6 6 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split(), noc=1, nop=2)
+    i0, i1, _ = synth.synthetic_pair(1100, 72, 1, seed=11, amp=2.0)
+    pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
+    ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    try:
+        ctx.set_option("sor_max_cluster", 16)
+    except api.OfdisError:
+        ctx.close()
+        pytest.skip("device grants no 16-CTA clusters")
+    ctx.upload_pyramids(0, pyr)
+    ctx.run(1)
+    assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "run h=1100, cluster 16")
+    ctx.close()
 
 
 def test_full_size_rgb_op3_l1_cost_vs_oracle(api, oracle_port):
