@@ -12,10 +12,16 @@ per pair.
 
   value : device-timed, padded pyramids already resident in HBM; the K steps are dealt round-robin
           to 8-10 lanes (context + stream) so that consecutive steps overlap
-  e2e   : same metric through the C-ABI with pinned HOST buffers; every step copies its input
-          (default: the un-padded finest-level images, the rest of the pyramid is derived on the
-          device inside the timed region; --e2e-upload pyramids ships what OFClass takes) and its
-          flows; the result is checked bit for bit against the resident path
+  e2e   : same metric through the C-ABI with pinned HOST buffers; every step copies its input and its
+          result.  Three legs (e2e.legs): "pyramids" = the strict OFClass contract (all four padded
+          float arrays of every level in, flow of level sc_l out; oflow.h:84-86) -- this is e2e.value,
+          the region the reference arm times; "finest" = un-padded finest-level images in (rest of the
+          pyramid derived on the device inside the timed region); "cli" = 8-bit frames in,
+          full-resolution flow out (what run_OF_INT does between imread and SaveFlowFile).  The
+          pyramids/finest results are checked bit for bit against the resident path
+  sharded : BASELINE configs[3] as written -- 64 pairs TOTAL owned by rank 0, scattered over the ranks'
+          GPUs with NCCL, gathered back (strong scaling; of_dis_b200/sharding.py)
+  big_configs : BASELINE configs[2] and [4] (1920x1080 RGB, 2880x1988 stereo) on one GPU, per kernel class
   single_lane / batch_sweep : one lane, L2 flushed before every step (latency of 64, 8, 1 pairs)
   roofline     : dominant kernel (lexicographic SOR), algorithmic bytes / CUDA-event time, plus the
                  issue-slot utilisation of the whole overlapped step
@@ -43,17 +49,21 @@ import numpy as np  # noqa: E402
 H_ORG, W_ORG = 436, 1024
 OP_POINT = 2
 MAX_DISTINCT = 16
+FRAMES_U8 = []  # the 8-bit frames of the pairs make_pairs() returned last ([2][h][w] each)
 
 
 def make_pairs(n, seed0):
     from of_dis_b200 import params, preprocess, synth
 
+    del FRAMES_U8[:]
     prm = params.operating_point(OP_POINT, W_ORG)
     pyrs = []
     for s in range(min(n, MAX_DISTINCT)):
         i0, i1, _ = synth.synthetic_pair(H_ORG, W_ORG, 1, seed=seed0 + s)
         pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
+        FRAMES_U8.append(np.stack([i0, i1]))
     while len(pyrs) < n:  # large batches cycle through the distinct pairs (generation costs 0.3 s each)
+        FRAMES_U8.append(FRAMES_U8[len(pyrs) % MAX_DISTINCT])
         pyrs.append(pyrs[len(pyrs) % MAX_DISTINCT])
     return prm, pyrs
 
@@ -117,28 +127,74 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_mpix(prm, pyrs, seconds, threads):
-    """Frame-parallel reference CPU build: `threads` workers, each running whole pairs
-    (OFClass instances share no mutable state).  Returns (Mpix/s, kind, n_pairs)."""
-    from concurrent.futures import ThreadPoolExecutor
-
+def _ref_kind(prm):
     from oracle import port_driver, ref_driver
 
     if ref_driver.ref_available(prm.flavour()):
-        kind, fn = "reference", ref_driver.ref_run
-    else:
-        kind, fn = "port", port_driver.port_run
-        port_driver.build()
+        return "reference", ref_driver
+    port_driver.build()
+    return "port", port_driver
+
+
+def _native_pass_seconds(pyrs, prm, nrep, threads):
+    """One call = nrep passes over pyrs on a native std::thread pool (oracle/ref_wrapper.cpp:
+    ofdis_ref_run_many); no Python inside the timed region."""
+    from oracle import ref_driver
+
+    return ref_driver.ref_run_many(pyrs, prm, nrep, threads)[0]
+
+
+def _python_pool_mpix(fn, prm, pyrs, seconds, threads):
+    """Round-1 harness kept for comparison: one ctypes call per pair from a Python thread pool."""
+    from concurrent.futures import ThreadPoolExecutor
+
     fn(pyrs[0], prm)  # warm
     done = 0
-    work = [pyrs[i % len(pyrs)] for i in range(max(len(pyrs), threads))]  # at least one pair per thread
+    work = [pyrs[i % len(pyrs)] for i in range(max(len(pyrs), threads))]
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
         while time.perf_counter() - t0 < seconds:
             list(ex.map(lambda p: fn(p, prm), work))
             done += len(work)
-    dt = time.perf_counter() - t0
-    return done * H_ORG * W_ORG / dt / 1e6, kind, done
+    return done * H_ORG * W_ORG / (time.perf_counter() - t0) / 1e6, done
+
+
+def cpu_reference(prm, pyrs, frames_u8, seconds, threads):
+    """Frame-parallel reference CPU build on `threads` host threads (OFClass instances share no mutable
+    state).  Returns the cpu_baseline object: OFClass region on 1 and on all threads (native
+    pool), the scaling factor, the CLI-level leg (pyramid + OFClass + upsampling) and, for comparison,
+    the round-1 Python-thread harness."""
+    kind, drv = _ref_kind(prm)
+    pix = H_ORG * W_ORG
+    if kind != "reference":  # no compiled reference here: the C port through the Python pool
+        val, done = _python_pool_mpix(drv.port_run, prm, pyrs, seconds, threads)
+        return {"value": val, "unit": "Mpix/s", "cores": threads, "kind": kind,
+                "sample": "%d pairs, frame-parallel Python pool over %d threads" % (done, threads)}
+    work = [pyrs[i % len(pyrs)] for i in range(max(len(pyrs), threads))]
+    _native_pass_seconds(work[:threads], prm, 1, threads)  # warm
+    # one thread: a few pairs; all threads: passes over `work` until `seconds` are used
+    t1 = _native_pass_seconds(work[:4], prm, 1, 1)
+    one = 4 * pix / t1 / 1e6
+    est = _native_pass_seconds(work, prm, 1, threads)
+    nrep = max(1, int(seconds * 0.5 / max(est, 1e-3)))
+    tn = _native_pass_seconds(work, prm, nrep, threads)
+    many = nrep * len(work) * pix / tn / 1e6
+    out = {"value": many, "unit": "Mpix/s", "cores": threads, "kind": kind,
+           "sample": "%d pairs of the same workload (OFClass ctor region), native std::thread pool over %d threads"
+                     % (nrep * len(work), threads),
+           "one_thread": one, "thread_scaling": many / one}
+    if frames_u8 is not None:
+        from oracle import ref_driver
+
+        fr = frames_u8[np.arange(len(work)) % len(frames_u8)]
+        ref_driver.ref_run_many_u8(fr[:threads], prm, 1, threads)
+        tc = ref_driver.ref_run_many_u8(fr, prm, 1, threads)[0]
+        out["cli"] = {"value": len(work) * pix / tc / 1e6, "unit": "Mpix/s",
+                      "sample": "8-bit frames -> pyramids -> OFClass -> full-resolution flow (run_dense.cpp:130-178,"
+                                "391-414 restated without OpenCV), %d pairs on %d threads" % (len(work), threads)}
+    pv, pdone = _python_pool_mpix(drv.ref_run, prm, pyrs, min(seconds * 0.3, 4.0), threads)
+    out["python_pool"] = {"value": pv, "note": "round-1 harness: one ctypes call per pair from a Python ThreadPoolExecutor"}
+    return out
 
 
 def run_reference_arm(args, rank, world):
@@ -151,22 +207,24 @@ def run_reference_arm(args, rank, world):
     threads = cores
     prm, pyrs0 = make_pairs(min(npairs, args.batch * world), 0)
     pyrs = [pyrs0[i % len(pyrs0)] for i in range(npairs)]
-    from concurrent.futures import ThreadPoolExecutor
-
-    from oracle import port_driver, ref_driver
-
-    if ref_driver.ref_available(prm.flavour()):
-        kind, fn = "reference", ref_driver.ref_run
-    else:
-        kind, fn = "port", port_driver.port_run
-        port_driver.build()
+    kind, drv = _ref_kind(prm)
     times = []
-    with ThreadPoolExecutor(max_workers=threads) as ex:
+    if kind == "reference":
         for s in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            list(ex.map(lambda p: fn(p, prm), pyrs))
+            t = _native_pass_seconds(pyrs, prm, 1, threads)
             if s >= args.warmup:
-                times.append(time.perf_counter() - t0)
+                times.append(t)
+        how = "native std::thread pool"
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            for s in range(args.warmup + args.steps):
+                t0 = time.perf_counter()
+                list(ex.map(lambda p: drv.port_run(p, prm), pyrs))
+                if s >= args.warmup:
+                    times.append(time.perf_counter() - t0)
+        how = "Python thread pool"
     ms = 1e3 * sum(times) / len(times)
     val = npairs * H_ORG * W_ORG / (ms * 1e-3) / 1e6
     line = {
@@ -175,8 +233,8 @@ def run_reference_arm(args, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
         "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": threads, "kind": kind,
-                         "sample": "%d pairs per step, frame-parallel over %d threads (host has %d cores), "
-                                   "timer = OFClass ctor region" % (npairs, threads, cores)},
+                         "sample": "%d pairs per step, frame-parallel over %d threads (%s; host has %d cores), "
+                                   "timer = OFClass ctor region" % (npairs, threads, how, cores)},
         "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -192,6 +250,73 @@ def workload_config(args, world):
                   "single_lane and batch_sweep numbers are taken with L2 flushed (256 MiB write) before every step"}
 
 
+def measure_sharded(args, prm, rank, world, local, stream, barrier, maxrank):
+    """BASELINE configs[3] as written (strong scaling): 64 pairs TOTAL in rank 0's pinned memory ->
+    H2D on rank 0 -> NCCL scatter -> engine on every rank's block -> NCCL gather -> D2H on rank 0, all
+    inside the timed region (CUDA events on the stream, max over ranks)."""
+    import torch
+
+    from of_dis_b200 import sharding
+
+    n_total = 64
+    out = {"pairs_total": n_total, "scaling": "strong", "ranks": world}
+    dev = torch.device("cuda", local)
+    for io in ("ofclass", "cli"):
+        eng = sharding.ShardedEngine(prm, n_total, W_ORG, H_ORG, io, dev, stream)
+        host_in = host_out = None
+        if rank == 0:
+            if io == "cli":
+                arr = np.stack([FRAMES_U8[i % len(FRAMES_U8)].reshape(-1) for i in range(n_total)])
+            else:
+                from of_dis_b200 import preprocess
+
+                rows = []
+                for i in range(min(n_total, MAX_DISTINCT)):
+                    a, b = FRAMES_U8[i % len(FRAMES_U8)]
+                    p = preprocess.PairPyramids(a, b, prm.sc_f, prm.p_samp_s)
+                    P_ = p.imgpadding
+                    rows.append(np.stack([p.i0[prm.sc_l][P_:-P_, P_:-P_], p.i1[prm.sc_l][P_:-P_, P_:-P_]]).reshape(-1))
+                arr = np.stack([rows[i % len(rows)] for i in range(n_total)])
+            host_in = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+            host_out = torch.empty((n_total, eng.out_elems), dtype=torch.float32).pin_memory()
+        for _ in range(args.warmup):
+            eng.step(host_in, host_out)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            eng.step(host_in, host_out)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ms = maxrank(ev0.elapsed_time(ev1) / args.steps)
+        barrier()
+        out[io] = {"ms_per_step": ms, "value": n_total * H_ORG * W_ORG / (ms * 1e-3) / 1e6, "unit": "Mpix/s",
+                   "h2d_bytes_per_step": int(n_total * eng.in_elems * (1 if io == "cli" else 4)),
+                   "d2h_bytes_per_step": int(n_total * eng.out_elems * 4), "pairs_per_rank": eng.m,
+                   "launches_per_step": None}
+        eng.close()
+    out["note"] = ("one stream per rank, steps back to back (no overlap between steps): rank 0's PCIe link carries all "
+                   "inputs and all flows; 'ofclass' = finest-level float images in / level flow out, 'cli' = 8-bit frames "
+                   "in / full-resolution flow out")
+    return out
+
+
+def measure_big_configs():
+    """BASELINE configs[2] and configs[4] on this GPU (tools/big_configs.py): step time, per kernel
+    class and per level; the SOR of configs[4]'s level 1 at 8 pairs is the launch SURVEY 8(d) names."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import big_configs
+
+        rows = []
+        for name, c in big_configs.CFGS.items():
+            for b in (1, 8):
+                rows.append(big_configs.measure(name, c, b, {}))
+        return rows
+    except Exception as e:  # must not lose the headline numbers
+        return {"error": str(e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,9 +328,11 @@ def main():
     ap.add_argument("--lanes", type=int, default=0,
                     help="contexts/streams whose steps overlap; 0 = 8, or the divisor of --steps in 6..12 closest to 8 "
                          "(every lane then runs the same number of steps and the drain is shortest)")
-    ap.add_argument("--e2e-upload", choices=("finest", "images", "pyramids"), default="finest",
-                    help="e2e H2D payload: I0,I1 of the finest used level (coarser levels, gradients and paddings derived "
-                         "on the device), I0,I1 of every level, or all four arrays of every level as OFClass takes them")
+    ap.add_argument("--e2e-upload", choices=("finest", "images", "pyramids", "cli"), default="pyramids",
+                    help="which leg becomes e2e.value: pyramids = all four padded arrays of every level as OFClass takes "
+                         "them (default: the region the reference arm times), finest = un-padded I0,I1 of the finest used "
+                         "level, images = padded I0,I1 of every level, cli = 8-bit frames in / full-resolution flow out")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sharded and big_configs legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.lanes <= 0:
@@ -273,13 +400,13 @@ def main():
     # device -- copies of one step under the kernels of the others, and the latency-bound refinement
     # kernels of several batches side by side (one batch of 64 pairs occupies 64 of 148 SMs there).
     NL = max(1, args.lanes)
-    lanes = [(ctx, stream, host_out)]
+    lanes = [(ctx, stream, host_out)]  # + the cli leg's full-resolution host buffer, appended below
     for _ in range(NL - 1):
         st_l = torch.cuda.Stream()
         lanes.append((api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, B, device=local,
                                   stream=st_l.cuda_stream), st_l,
                       torch.empty((B, flow_floats), dtype=torch.float32).pin_memory()))
-    for c, _, _ in lanes:
+    for c in [l[0] for l in lanes]:
         c.upload_packed(0, B, host_in.data_ptr())
         c.set_graph_mode(True)
 
@@ -287,12 +414,12 @@ def main():
         """K steps dealt round-robin to the lanes; device time from one event pair spanning all streams."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
-        for _, st_l, _ in lanes[1:]:
-            st_l.wait_event(ev0)
+        for l in lanes[1:]:
+            l[1].wait_event(ev0)
         for i in range(steps):
             step_fn(i)
-        for _, st_l, _ in lanes[1:]:
-            stream.wait_stream(st_l)
+        for l in lanes[1:]:
+            stream.wait_stream(l[1])
         ev1.record(stream)
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / steps
@@ -307,10 +434,10 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
-    l0 = sum(c.launch_count for c, _, _ in lanes)
+    l0 = sum(l[0].launch_count for l in lanes)
     t0 = time.time()
     ms_res = maxrank(pipelined(resident_step, args.steps))
-    launches = (sum(c.launch_count for c, _, _ in lanes) - l0) // args.steps
+    launches = (sum(l[0].launch_count for l in lanes) - l0) // args.steps
     barrier()
     # one lane alone, L2 flushed before every step (latency of one batch)
     ms_res_single = maxrank(timed(lambda: ctx.run(B), args.steps))
@@ -332,65 +459,100 @@ def main():
     for f, p in enumerate(pyrs):
         fin = np.stack([p.i0[prm.sc_l][P_:-P_, P_:-P_], p.i1[prm.sc_l][P_:-P_, P_:-P_]])
         host_fin[f].numpy()[:] = fin.reshape(-1)
-    mode = args.e2e_upload
-    h2d_floats = {"finest": n_fin, "images": n_img, "pyramids": ff}[mode]
-    h2d_payload = {"finest": "un-padded I0,I1 of level %d; levels %d..%d, I0x,I0y and paddings derived on the device "
-                             "inside the timed region" % (prm.sc_l, prm.sc_l + 1, prm.sc_f),
-                   "images": "padded I0,I1 of levels %d..%d; I0x,I0y derived on the device inside the timed region"
-                             % (prm.sc_l, prm.sc_f),
-                   "pyramids": "padded I0,I0x,I0y,I1 of levels %d..%d" % (prm.sc_l, prm.sc_f)}[mode]
+    host_u8 = torch.from_numpy(np.ascontiguousarray(np.stack(FRAMES_U8[:B]))).pin_memory()  # [B][2][h][w]
+    full_floats = H_ORG * W_ORG * prm.nop
+    for i in range(NL):  # full-resolution output buffers of the cli leg, one per lane
+        lanes[i] = lanes[i] + (torch.empty((B, full_floats), dtype=torch.float32).pin_memory(),)
+    payloads = {
+        "finest": (n_fin * 4, flow_floats * 4, "un-padded I0,I1 of level %d in; levels %d..%d, I0x,I0y and paddings derived on "
+                   "the device inside the timed region; flow of level %d out" % (prm.sc_l, prm.sc_l + 1, prm.sc_f, prm.sc_l)),
+        "images": (n_img * 4, flow_floats * 4, "padded I0,I1 of levels %d..%d in; I0x,I0y derived on the device inside the "
+                   "timed region; flow of level %d out" % (prm.sc_l, prm.sc_f, prm.sc_l)),
+        "pyramids": (ff * 4, flow_floats * 4, "padded I0,I0x,I0y,I1 of levels %d..%d in (what OFClass takes, oflow.h:84-86); "
+                     "flow of level %d out" % (prm.sc_l, prm.sc_f, prm.sc_l)),
+        "cli": (2 * H_ORG * W_ORG, full_floats * 4, "8-bit frames in (pyramid, gradients, paddings on the device); "
+                "full-resolution flow out (x%d upsampling and crop on the device): run_dense.cpp:130-178,391-414" % (1 << prm.sc_l)),
+    }
 
-    def upload(c, b=B):
+    def upload(c, mode, b=B):
         if mode == "finest":
             c.upload_finest_level(0, b, host_fin.data_ptr())
         elif mode == "images":
             c.upload_packed_images(0, b, host_img.data_ptr())
+        elif mode == "cli":
+            c.upload_frames_u8(0, b, host_u8.data_ptr(), W_ORG, H_ORG)
         else:
             c.upload_packed(0, b, host_in.data_ptr())
 
-    def e2e_step(i):
-        c, _, ho = lanes[i % NL]
-        upload(c)
-        c.run(B)
-        c.get_flow_batch(0, B, ho.data_ptr())
+    def download(c, mode, ho, hfull, b=B):
+        if mode == "cli":
+            c.get_flow_fullres(0, b, hfull.data_ptr(), W_ORG, H_ORG)
+        else:
+            c.get_flow_batch(0, b, ho.data_ptr())
 
-    # Warm-up: W steps per lane, continued until 0.4 s of copies have run -- an idle PCIe link takes
-    # ~0.2 s of traffic to leave its low-power state (tools/e2e_probe.py: first pass 30 GB/s, then 54).
-    n_warm_e2e, w_start = 0, time.perf_counter()
-    while n_warm_e2e < NL * args.warmup or time.perf_counter() - w_start < 0.4:
-        e2e_step(n_warm_e2e)
-        n_warm_e2e += 1
-        if n_warm_e2e % NL == 0:
-            torch.cuda.synchronize()
-    barrier()
     # the e2e path must produce the flows of the resident path (same pairs), bit for bit
     resident_flow = torch.empty((B, flow_floats), dtype=torch.float32)
     ctx.upload_packed(0, B, host_in.data_ptr())
     ctx.run(B)
     ctx.get_flow_batch(0, B, resident_flow.data_ptr())
     ctx.sync()
-    e2e_step(0)
-    torch.cuda.synchronize()
-    e2e_same = bool(torch.equal(resident_flow.view(torch.int32), host_out.view(torch.int32)))
-    barrier()
-    w0 = time.perf_counter()
-    ms_e2e = maxrank(pipelined(e2e_step, args.steps))
-    wall_e2e = (time.perf_counter() - w0) / args.steps * 1e3
-    barrier()
+    from of_dis_b200 import preprocess as _pp
+
+    def measure_e2e(mode):
+        def e2e_step(i):
+            c, _, ho, hfull = lanes[i % NL]
+            upload(c, mode)
+            c.run(B)
+            download(c, mode, ho, hfull)
+
+        # Warm-up: W steps per lane, continued until 0.4 s of copies have run -- an idle PCIe link takes
+        # ~0.2 s of traffic to leave its low-power state (tools/e2e_probe.py: first pass 30 GB/s, then 54).
+        n_warm, w_start = 0, time.perf_counter()
+        while n_warm < NL * args.warmup or time.perf_counter() - w_start < 0.4:
+            e2e_step(n_warm)
+            n_warm += 1
+            if n_warm % NL == 0:
+                torch.cuda.synchronize()
+        barrier()
+        e2e_step(0)
+        torch.cuda.synchronize()
+        if mode == "cli":
+            exp = _pp.postprocess(resident_flow[0].numpy().reshape(li["h"], li["w"], prm.nop), prm.sc_l, pyrs[0].padw,
+                                  pyrs[0].padh, W_ORG, H_ORG)
+            same = bool(np.array_equal(lanes[0][3][0].numpy().view(np.uint32), np.ascontiguousarray(exp).reshape(-1).view(np.uint32)))
+        else:
+            same = bool(torch.equal(resident_flow.view(torch.int32), host_out.view(torch.int32)))
+        barrier()
+        w0 = time.perf_counter()
+        ms = maxrank(pipelined(e2e_step, args.steps))
+        wall = (time.perf_counter() - w0) / args.steps * 1e3
+        barrier()
+        h2d, d2h, what = payloads[mode]
+        return {"value": B * world * H_ORG * W_ORG / (ms * 1e-3) / 1e6, "ms_per_step": ms, "wall_ms_per_step": wall,
+                "h2d_bytes_per_step": int(B * h2d), "d2h_bytes_per_step": int(B * d2h), "payload": what,
+                "result_checked_bitwise": same, "warmup_steps": n_warm}
+
+    mode = args.e2e_upload
+    legs = {m: measure_e2e(m) for m in dict.fromkeys([mode, "pyramids", "finest", "cli"])}
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
 
     # serial variant: one lane, H2D -> run -> D2H back to back, L2 flushed between steps
     def e2e_serial():
-        upload(ctx)
+        upload(ctx, mode)
         ctx.run(B)
-        ctx.get_flow_batch(0, B, host_out.data_ptr())
+        download(ctx, mode, host_out, lanes[0][3])
 
     for _ in range(args.warmup):
         e2e_serial()
     ms_e2e_serial = maxrank(timed(e2e_serial, args.steps))
-    for c, _, _ in lanes[1:]:
+    for c in [l[0] for l in lanes[1:]]:
         c.close()
+
+    # ---- BASELINE configs[3] as written: 64 pairs in total, scattered from rank 0 over NCCL ----
+    sharded = None
+    if not args.no_extras:
+        sharded = measure_sharded(args, prm, rank, world, local, stream, barrier, maxrank)
 
     if rank != 0:
         ctx.close()
@@ -400,7 +562,6 @@ def main():
 
     pix = B * world * H_ORG * W_ORG
     value = pix / (ms_res * 1e-3) / 1e6
-    e2e_val = pix / (ms_e2e * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (SOR), measured live with CUDA events ----
     ctx.set_graph_mode(False)
@@ -428,7 +589,7 @@ def main():
                 issue = {"warp_instructions_per_step": wi, "sms": sms, "sm_mhz": clocks["sm_mhz"],
                          "issue_slot_utilisation": wi / (ms_res * 1e-3 * sms * 4 * clocks["sm_mhz"] * 1e6),
                          "ipc_per_sm": wi / (ms_res * 1e-3 * sms * clocks["sm_mhz"] * 1e6)}
-        roof = {"bound": "hbm", "kernel": "sor_tma_kernel (lexicographic SOR wavefront, all sweeps fused; sor_kernel on levels that exceed its shared-memory budget)", "achieved": ach,
+        roof = {"bound": "hbm", "kernel": "sor_wave_kernel (lexicographic SOR wavefront, all sweeps fused, one CTA per frame at this level size)", "achieved": ach,
                 "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_note": "ncu dram bytes per SOR launch with caches flushed before every replay; "
                 "2.99e6 with --cache-control none (profiles/roofline_traffic.json)", "issue": issue, "peak_source": how,
                 "algorithmic_bytes_per_step": alg, "kernel_ms_per_step": sor["ms_per_step"],
@@ -453,9 +614,9 @@ def main():
             ms = timed(lambda: c2.run(b), 10)
 
             def e2e_b():
-                upload(c2, b)
+                upload(c2, mode, b)
                 c2.run(b)
-                c2.get_flow_batch(0, b, host_out.data_ptr())
+                download(c2, mode, host_out, lanes[0][3], b)
 
             for _ in range(3):  # the first upload allocates the context's staging buffer
                 e2e_b()
@@ -467,7 +628,17 @@ def main():
     numa.unbind(prev_affinity)  # the CPU baseline uses every core of the host
     cores = os.cpu_count() or 1
     threads = cores
-    cpu_val, kind, done = cpu_reference_mpix(prm, pyrs, args.cpu_seconds, threads) if world == 1 else (None, None, 0)
+    frames_u8 = np.ascontiguousarray(np.stack(FRAMES_U8[:min(B, MAX_DISTINCT)]))[..., None]  # [n][2][h][w][1]
+    cpu = cpu_reference(prm, pyrs, frames_u8, args.cpu_seconds, threads) if world == 1 else None
+    big = None
+    if world == 1 and not args.no_extras:
+        big = measure_big_configs()
+    lead = dict(legs[mode])
+    lead.update({"unit": "Mpix/s", "leg": mode, "host_numa_node": numa_node,
+                 "flows_equal_resident_path": legs[mode]["result_checked_bitwise"],
+                 "mode": "%d lanes (context+stream), step i on lane i %% lanes: copies and kernels of consecutive steps overlap" % NL,
+                 "serial_ms_per_step": ms_e2e_serial, "serial_value": pix / (ms_e2e_serial * 1e-3) / 1e6,
+                 "legs": legs})
     line = {
         "metric": "Mpix/s dense flow (1024x436, op-point 2)", "value": value, "unit": "Mpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True,
@@ -475,19 +646,12 @@ def main():
         "config": workload_config(args, world),
         "single_lane": {"ms_per_step": ms_res_single, "value": pix / (ms_res_single * 1e-3) / 1e6,
                         "note": "one context, one stream, L2 flushed before every step"},
-        "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
-                "h2d_bytes_per_step": int(B * h2d_floats * 4), "h2d_payload": h2d_payload,
-                "host_numa_node": numa_node, "warmup_steps": n_warm_e2e, "flows_equal_resident_path": e2e_same, "d2h_bytes_per_step": int(B * flow_floats * 4),
-                "mode": "%d lanes (context+stream), step i on lane i %% lanes: copies and kernels of consecutive steps overlap" % NL,
-                "serial_ms_per_step": ms_e2e_serial,
-                "serial_value": pix / (ms_e2e_serial * 1e-3) / 1e6},
+        "e2e": lead,
         "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
-        "clocks": clocks, "roofline": roof, "batch_sweep": sweep,
+        "clocks": clocks, "roofline": roof, "batch_sweep": sweep, "sharded": sharded, "big_configs": big,
     }
-    if cpu_val is not None:
-        line["cpu_baseline"] = {"value": cpu_val, "unit": "Mpix/s", "cores": threads, "kind": kind,
-                                "sample": "%d pairs of the same workload, frame-parallel over %d threads for %.0f s "
-                                          "(host has %d cores)" % (done, threads, args.cpu_seconds, cores)}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
     print(json.dumps(line))
     ctx.close()
     if world > 1:

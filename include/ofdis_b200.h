@@ -15,7 +15,8 @@
  *     (PatClass::InitializePatch, OptimizeIter  patch.cpp:57-88,119-212 -- fused into the same kernel)
  *   PatGridClass::AggregateFlowDense patchgrid.cpp:213-397  ofdis_patgrid_aggregate
  *   PatGridClass::SetComplGrid       patchgrid.h:36 + oflow.cpp:162-170   ofdis_params.usefbcon = 1 (both grids of a pair
- *                                                            live in the context; ofdis_upload_level_fb)
+ *                                                            live in the context; ofdis_upload_level_fb,
+ *                                                            ofdis_set_direction)
  *   PatGridClass::GetQuePatchDis &c  patchgrid.h:42-44      ofdis_get_patches
  *   VarRefClass::VarRefClass         refine_variational.h:37-39,    ofdis_varref_refine
  *                                    refine_variational.cpp:25-116
@@ -185,6 +186,12 @@ int ofdis_profile_run(ofdis_ctx* ctx, int nframes, int steps, double* ms_by_clas
 /* The same, additionally split by pyramid level: ms_by_level_class[(level - sc_l) * 5 + class] (may be NULL). */
 int ofdis_profile_levels(ofdis_ctx* ctx, int nframes, int steps, double* ms_by_class, long* launches_by_class,
                          double* ms_by_level_class);
+/* usefbcon contexts only: address ONE grid of every pair (0 = forward, 1 = the grid on the swapped images)
+ * in the following ofdis_patgrid_optimize / ofdis_patgrid_aggregate (one frame per call) / ofdis_set_flow /
+ * ofdis_get_flow / ofdis_get_patches calls; -1 (default) restores "both grids; flows and patches of the
+ * forward one".  This is what two stand-alone PatGridClass objects joined by SetComplGrid
+ * (patchgrid.h:36, oflow.cpp:162-170) are built on. */
+int ofdis_set_direction(ofdis_ctx* ctx, int dir);
 /* Launch-geometry options (tuning / test hook, results are bit-identical under every setting):
  *   "sor_single_max"  32 | 64 | 128 (default): refinement levels of up to this many rows run their SOR in
  *                     one CTA, taller ones in a thread-block cluster of row bands (sor_wave_kernel.cuh)

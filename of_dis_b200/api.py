@@ -30,7 +30,7 @@ EXPORTS = [
     "ofdis_debug_varref_iters", "ofdis_launch_count", "ofdis_set_graph_mode", "ofdis_profile_run",
     "ofdis_set_camlr", "ofdis_set_dp_thresh_sq", "ofdis_packed_images_frame_floats", "ofdis_upload_packed_images",
     "ofdis_upload_frames_u8", "ofdis_finest_level_frame_floats", "ofdis_upload_finest_level", "ofdis_get_flow_fullres",
-    "ofdis_get_level", "ofdis_upload_level_fb", "ofdis_set_option", "ofdis_profile_levels",
+    "ofdis_get_level", "ofdis_upload_level_fb", "ofdis_set_option", "ofdis_profile_levels", "ofdis_set_direction",
 ]
 
 
@@ -90,6 +90,7 @@ def lib():
         L.ofdis_debug_get.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
         L.ofdis_set_graph_mode.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.ofdis_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+        L.ofdis_set_direction.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.ofdis_set_camlr.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.ofdis_set_dp_thresh_sq.argtypes = [ctypes.c_void_p, ctypes.c_float]
         L.ofdis_profile_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]

@@ -26,6 +26,7 @@ struct ofdis_ctx {
   // images); dirs = 2, cap = max_frames * dirs internal frames are allocated
   int dirs = 1, cap = 0;
   int last_vr_fstep = 1;
+  int sel_dir = -1;                // ofdis_set_direction: -1 = both directions / the forward grid
   // SOR band plan (sor_band_plan): levels of up to sor_single_max rows run in one CTA, taller ones in a
   // cluster of up to sor_max_cluster CTAs (8 = portable limit; 16 where the device grants it)
   int sor_single_max = 128, sor_max_cluster = 8, sor_dev_cluster = 8;
@@ -293,6 +294,8 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
     const size_t per_frame = plane * (1 + C + 8 * C) + diag * 4 * (8 + 2);
     ok = dalloc((void**)&ctx->d_planes, sizeof(float) * per_frame * cap);
     if (ok) {
+      // never-written record slots (wavefront ramps, padded rows) are read by idle SOR lanes: keep them finite
+      cudaMemsetAsync(ctx->d_planes, 0, sizeof(float) * per_frame * cap, ctx->stream);
       float* q = ctx->d_planes;
       VarRefPlanes& P = ctx->planes;
       P.rec = reinterpret_cast<float4*>(q); q += diag * 4 * 8 * cap;   // records first (alignment)
@@ -580,7 +583,10 @@ int ofdis_patgrid_optimize(ofdis_ctx* ctx, int level, int f0, int f1, int init_f
   LevelGeom* L = level_of(ctx, level);
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_optimize: bad argument");
   CK(cudaSetDevice(ctx->device));
-  const int n = launch_patch_optimize(*L, ctx->pp, f0 * ctx->dirs, f1 * ctx->dirs, init_from_coarser != 0, ctx->stream, ctx->prof);
+  if (ctx->sel_dir >= 0 && f1 != f0 + 1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_optimize: one frame at a time while a direction is selected");
+  const int q0 = ctx->sel_dir >= 0 ? f0 * ctx->dirs + ctx->sel_dir : f0 * ctx->dirs;
+  const int q1 = ctx->sel_dir >= 0 ? q0 + 1 : f1 * ctx->dirs;
+  const int n = launch_patch_optimize(*L, ctx->pp, q0, q1, init_from_coarser != 0, ctx->stream, ctx->prof);
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "patch_optimize_kernel launch", cudaGetLastError());
   ctx->launches += n;
   return OFDIS_OK;
@@ -596,8 +602,11 @@ int ofdis_patgrid_aggregate(ofdis_ctx* ctx, int level, int f0, int f1) {
     // both grids' patch positions first; the backward flow is not densified on the last level (oflow.cpp:269-270)
     if (launch_fb_prepare(*L, f0 * 2, f1 * 2, ctx->stream) < 0) return fail(ctx, OFDIS_ERR_CUDA, "fb_prepare_kernel launch", cudaGetLastError());
     ctx->launches += 1;
-    n = (level == ctx->prm.sc_l) ? launch_densify(stepped(*L, 2), f0 * 2, f0 * 2 + (f1 - f0), ctx->stream, ctx->prof)
-                                 : launch_densify(*L, f0 * 2, f1 * 2, ctx->stream, ctx->prof);
+    if (ctx->sel_dir >= 0)  // one grid of the couple (PatGridClass::AggregateFlowDense of either stand-alone grid)
+      n = launch_densify(stepped(*L, 2), f0 * 2 + ctx->sel_dir, f0 * 2 + ctx->sel_dir + (f1 - f0), ctx->stream, ctx->prof);
+    else
+      n = (level == ctx->prm.sc_l) ? launch_densify(stepped(*L, 2), f0 * 2, f0 * 2 + (f1 - f0), ctx->stream, ctx->prof)
+                                   : launch_densify(*L, f0 * 2, f1 * 2, ctx->stream, ctx->prof);
   } else {
     n = launch_densify(*L, f0, f1, ctx->stream, ctx->prof);
   }
@@ -646,6 +655,12 @@ int ofdis_varref_refine(ofdis_ctx* ctx, int level, int f0, int f1) { return varr
 
 int ofdis_debug_varref_iters(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner) {
   return varref_impl(ctx, level, f0, f1, n_inner);
+}
+
+int ofdis_set_direction(ofdis_ctx* ctx, int dir) {
+  if (!ctx || dir < -1 || dir > 1 || (dir >= 0 && ctx->dirs != 2)) return OFDIS_ERR_ARG;
+  ctx->sel_dir = dir;
+  return OFDIS_OK;
 }
 
 int ofdis_set_option(ofdis_ctx* ctx, const char* name, int value) {
@@ -719,8 +734,8 @@ int ofdis_get_flow(ofdis_ctx* ctx, int frame, int level, float* dst, int memkind
   if (!ctx) return OFDIS_ERR_ARG;
   const int li = flow_index(ctx, level);
   if (li < 0 || frame < 0 || frame >= ctx->max_frames || !dst) return fail(ctx, OFDIS_ERR_ARG, "get_flow: bad argument");
-  CK(cudaMemcpyAsync(dst, ctx->d_flow[li] + (size_t)frame * ctx->dirs * ctx->flow_floats[li], sizeof(float) * ctx->flow_floats[li],
-                     kind_out(memkind), ctx->stream));
+  CK(cudaMemcpyAsync(dst, ctx->d_flow[li] + (size_t)(frame * ctx->dirs + std::max(ctx->sel_dir, 0)) * ctx->flow_floats[li],
+                     sizeof(float) * ctx->flow_floats[li], kind_out(memkind), ctx->stream));
   if (memkind == OFDIS_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
   return OFDIS_OK;
 }
@@ -729,8 +744,8 @@ int ofdis_set_flow(ofdis_ctx* ctx, int frame, int level, const float* src, int m
   if (!ctx) return OFDIS_ERR_ARG;
   const int li = flow_index(ctx, level);
   if (li < 0 || frame < 0 || frame >= ctx->max_frames || !src) return fail(ctx, OFDIS_ERR_ARG, "set_flow: bad argument");
-  CK(cudaMemcpyAsync(ctx->d_flow[li] + (size_t)frame * ctx->dirs * ctx->flow_floats[li], src, sizeof(float) * ctx->flow_floats[li],
-                     kind_in(memkind), ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_flow[li] + (size_t)(frame * ctx->dirs + std::max(ctx->sel_dir, 0)) * ctx->flow_floats[li], src,
+                     sizeof(float) * ctx->flow_floats[li], kind_in(memkind), ctx->stream));
   return OFDIS_OK;
 }
 
@@ -751,7 +766,7 @@ int ofdis_get_patches(ofdis_ctx* ctx, int frame, int level, float* p, float* pwe
   LevelGeom* L = level_of(ctx, level);
   if (!L || frame < 0 || frame >= ctx->max_frames) return fail(ctx, OFDIS_ERR_ARG, "get_patches: bad argument");
   const size_t np = L->np;
-  frame *= ctx->dirs;  // the forward grid
+  frame = frame * ctx->dirs + std::max(ctx->sel_dir, 0);  // the forward grid unless a direction is selected
   if (p) CK(cudaMemcpyAsync(p, L->pat_p + frame * np * L->nop, sizeof(float) * np * L->nop, cudaMemcpyDeviceToHost, ctx->stream));
   if (pweight) CK(cudaMemcpyAsync(pweight, L->pat_w + frame * np * L->novals, sizeof(float) * np * L->novals, cudaMemcpyDeviceToHost, ctx->stream));
   if (conv) CK(cudaMemcpyAsync(conv, L->pat_conv + frame * np, sizeof(int) * np, cudaMemcpyDeviceToHost, ctx->stream));

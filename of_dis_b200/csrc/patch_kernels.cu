@@ -508,6 +508,298 @@ __global__ void __launch_bounds__(256) patch_p8c1_kernel(LevelGeom g, PatchParam
   }
 }
 
+// ---------------------------------------------------------------------------
+// Specialisation for P = 12 (operating points 3 and 4; gray and RGB): same 8-lanes-per-patch
+// mapping and reduction order as the generic kernel, but
+//   * the template and the residual of a lane (P*P*C/8 = 18 or 54 elements) live in registers, the
+//     template gradients too for gray (RGB keeps them in shared-memory columns);
+//   * the bilinear taps of I1 come from a per-patch WINDOW in shared memory -- the (P+1+2M)^2 pixels
+//     around the patch's current integer position (M = 2 pixels of slack; stereo: P+1 rows, the row
+//     never moves) -- staged by the patch's own 8 lanes and re-staged only when the position leaves
+//     the slack.  The generic kernel issues 4 LDGs per element and iteration whose 32 lanes touch 4
+//     patches x 1..2 sectors each: the L1 tag stage, not the math, bounded it (profiles/).  From
+//     shared memory the same taps are 4 LDS with at most a 2-way bank conflict between patches;
+//   * element offsets are walked incrementally (no offset table).
+// Arithmetic (operand order, reduction tree, stop tests) is that of patch_optimize_kernel.
+template <int C> struct PwCfg {
+  static constexpr int P = 12, M = 2, W = P + 1 + 2 * M, WC = W * C, PC = P * C, N = P * P * C, NK = N / 8;
+};
+
+template <int NOP, int C>
+__global__ void __launch_bounds__(256, C == 1 ? 2 : 1) patch_p12_kernel(LevelGeom g, PatchParams pp, int f0,
+                                                                        int init_from_coarser) {
+  using Cfg = PwCfg<C>;
+  constexpr int P = Cfg::P, M = Cfg::M, W = Cfg::W, WC = Cfg::WC, PC = Cfg::PC, NK = Cfg::NK;
+  constexpr int WH = (NOP == 2) ? W : P + 1;  // window rows
+  constexpr int WIN = WH * WC;                // floats per window
+  constexpr bool G_REG = (C == 1);            // template gradients in registers
+  extern __shared__ float smem[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int l8 = tid & 7;
+  const int frame = f0 + blockIdx.y;
+  const int ip = blockIdx.x * (nthr >> 3) + (tid >> 3);
+  const bool valid = ip < g.np;
+  const float fn = (float)Cfg::N;
+  float* const win = smem + (tid >> 3) * WIN;                  // this patch's window
+  float* const sGx = smem + (nthr >> 3) * WIN + tid;           // RGB: gradient columns [k][thread]
+  float* const sGy = sGx + NK * nthr;
+  const int rowC = g.tmp_w * C;
+
+  const float* i0 = g.img[0] + (size_t)frame * g.img_fs[0];
+  const float* i0x = g.img[1] + (size_t)frame * g.img_fs[1];
+  const float* i0y = g.img[2] + (size_t)frame * g.img_fs[2];
+  const float* i1 = g.img[3] + (size_t)frame * g.img_fs[3];
+
+  const int ipc = valid ? ip : 0;
+  const int gx_i = ipc / g.noph, gy_i = ipc - gx_i * g.noph;
+  const int cxi = gx_i * g.steps + g.offw, cyi = gy_i * g.steps + g.offh;
+  const float refx = (float)cxi, refy = (float)cyi;
+
+  // ---- K1: template, gradients, mean normalisation (patch.cpp:287-332) ------
+  float T[NK], R[NK], GX[G_REG ? NK : 1], GY[G_REG ? NK : 1];
+  {
+    const int base = ((cxi + g.pad - P / 2) + (cyi + g.pad - P / 2) * g.tmp_w) * C;
+    float acc = 0.f;
+    int rem = l8, off = l8;  // element e = l8 + 8k: rem = e mod P*C, off = image offset
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      T[k] = i0[base + off];
+      const float gx = i0x[base + off], gy = i0y[base + off];
+      if (G_REG) {
+        GX[k] = gx;
+        GY[k] = gy;
+      } else {
+        sGx[k * nthr] = gx;
+        sGy[k * nthr] = gy;
+      }
+      acc = (k == 0) ? T[k] : acc + T[k];
+      R[k] = 0.f;
+      rem += 8;
+      off += 8;
+      if (rem >= PC) {
+        rem -= PC;
+        off += rowC - PC;
+      }
+    }
+    if (pp.patnorm > 0) {
+      const float m = fold8(acc, 0.f, true, false) / fn;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) T[k] = T[k] - m;
+    }
+  }
+  // ---- Hessian and its Cholesky factor (patch.cpp:71-88) ---------------------
+  float L00, L10 = 0.f, L11 = 0.f;
+  {
+    float axx = 0.f, axy = 0.f, ayy = 0.f;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const float a = G_REG ? GX[k] : sGx[k * nthr], b = G_REG ? GY[k] : sGy[k * nthr];
+      const float vxx = a * a, vxy = a * b, vyy = b * b;
+      axx = (k == 0) ? vxx : axx + vxx;
+      axy = (k == 0) ? vxy : axy + vxy;
+      ayy = (k == 0) ? vyy : ayy + vyy;
+    }
+    float H00 = fold8(axx, 0.f, true, false);
+    if (NOP == 2) {
+      const float H01 = fold8(axy, 0.f, true, false);
+      float H11 = fold8(ayy, 0.f, true, false);
+      if (H00 * H11 - H01 * H01 == 0.f) {
+        H00 = (float)((double)H00 + 1e-10);
+        H11 = (float)((double)H11 + 1e-10);
+      }
+      L00 = H00; L10 = H01; L11 = H11;
+      if (H00 > 0.f) {
+        L00 = sqrtf(H00);
+        L10 = H01 / L00;
+        const float x = H11 - L10 * L10;
+        if (x > 0.f) L11 = sqrtf(x);
+      }
+    } else {
+      if (H00 == 0.f) H00 = (float)((double)H00 + 1e-10);
+      L00 = H00 > 0.f ? sqrtf(H00) : H00;
+    }
+  }
+  // ---- K2 (patchgrid.cpp:195-211) ---------------------------------------------
+  float pin0 = 0.f, pin1 = 0.f;
+  if (init_from_coarser && g.flow_prev != nullptr) {
+    const float* fp = g.flow_prev + (size_t)frame * g.flow_prev_frame_stride;
+    const int i = (cyi >> 1) * (g.w / 2) + (cxi >> 1);
+    if (NOP == 2) {
+      const float2 v = reinterpret_cast<const float2*>(fp)[i];
+      pin0 = v.x * 2.f;
+      pin1 = v.y * 2.f;
+    } else {
+      pin0 = fp[i] * 2.f;
+    }
+  }
+  // ---- K3 (patch.cpp:119-212, 264-284) ------------------------------------------
+  float p0 = pin0, p1 = pin1, dp0 = 0.f, dp1 = 0.f;
+  float ptx = refx + p0, pty = (NOP == 2) ? refy + p1 : refy;
+  const float stx = ptx, sty = pty;
+  float dpsq_init = 1e-10f, mares = 1e5f, mares_old = 1e20f;
+  int cnt = 0, conv = 0;
+  bool wrote_w = false, finishing = false, active = valid;
+  if (active && (ptx < g.lb || pty < g.lb || ptx > g.ubw || pty > g.ubh)) {
+    conv = 1;
+    active = false;
+  }
+  // window origin in padded-image pixels; far away = nothing staged yet
+  int wx0 = -(1 << 20), wy0 = -(1 << 20);
+
+  while (__any_sync(FULL, active)) {
+    float b0 = 0.f, b1 = 0.f, sw = 0.f;
+    {
+      float acc = 0.f;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+      int ux = 0, uy = 0;
+      bool restage = false;
+      if (active) {
+        const int pcx = (int)ceilf(ptx + .00001f), pcy = (int)ceilf(pty + .00001f);
+        const int pfx = (int)floorf(ptx), pfy = (int)floorf(pty);
+        const float rx = ptx - (float)pfx, ry = pty - (float)pfy;
+        w0 = rx * ry;
+        w1 = (1.f - rx) * ry;
+        w2 = rx * (1.f - ry);
+        w3 = (1.f - rx) * (1.f - ry);
+        // top-left tap of element (0,0): padded-image pixel (tx, ty)
+        const int tx = pcx + g.pad - P / 2 - 1, ty = pcy + g.pad - P / 2 - 1;
+        ux = tx - wx0;
+        uy = ty - wy0;
+        restage = (ux < 0) | (ux > 2 * M) | (uy < 0) | (uy > ((NOP == 2) ? 2 * M : 0));
+        if (restage) {
+          wx0 = tx - M;
+          wy0 = (NOP == 2) ? ty - M : ty;
+          ux = M;
+          uy = (NOP == 2) ? M : 0;
+        }
+      }
+      if (__any_sync(FULL, restage)) {
+        __syncwarp();  // every lane has finished reading the previous window
+        if (restage) {
+          const int xlo = wx0 * C, xmax = g.tmp_w * C - 1;
+          for (int idx = l8; idx < WIN; idx += 8) {
+            const int row = idx / WC, cc = idx - row * WC;
+            int sy = wy0 + row, sx = xlo + cc;  // coordinates outside the padded image are never used as taps
+            sy = sy < 0 ? 0 : (sy > g.tmp_h - 1 ? g.tmp_h - 1 : sy);
+            sx = sx < 0 ? 0 : (sx > xmax ? xmax : sx);
+            win[idx] = __ldg(i1 + (size_t)sy * rowC + sx);
+          }
+        }
+        __syncwarp();
+      }
+      if (active) {
+        const float* q = win + uy * WC + ux * C;  // tap d of element 0
+        int rem = l8, off = l8;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          const float* a = q + off;
+          const float v = w0 * a[WC + C] + w1 * a[WC] + w2 * a[C] + w3 * a[0];
+          R[k] = v;
+          acc = (k == 0) ? v : acc + v;
+          rem += 8;
+          off += 8;
+          if (rem >= PC) {
+            rem -= PC;
+            off += WC - PC;
+          }
+        }
+      }
+      float m = 0.f;
+      if (pp.patnorm > 0) m = fold8(acc, 0.f, true, false) / fn;
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          float d = R[k];
+          if (pp.patnorm > 0) d = d - m;
+          float r, w;
+          if (pp.costfct == 0) {
+            r = d - T[k];
+            w = fabsf(r);
+          } else if (pp.costfct == 1) {
+            const float t = d - T[k];
+            r = copysignf(sqrtf(fabsf(t)), t);
+            w = fabsf(r);
+          } else if (pp.costfct == 2) {
+            const float t = d - T[k];
+            const float hh = sqrtf((sqrtf(1.0f + (t * t) / 25.0f) - 1.0f) * 50.0f);
+            r = copysignf(hh, t);
+            w = fabsf(r);
+          } else {  // reference leaves pdiff/pweight untouched (patch.cpp:230-261)
+            r = d;
+            w = 0.f;
+          }
+          R[k] = r;
+          const float gx = G_REG ? GX[k] : sGx[k * nthr], gy = G_REG ? GY[k] : sGy[k * nthr];
+          const float vx = gx * r, vy = gy * r;
+          b0 = (k == 0) ? vx : b0 + vx;
+          b1 = (k == 0) ? vy : b1 + vy;
+          sw = (k == 0) ? w : sw + w;
+        }
+        wrote_w = (pp.costfct >= 0 && pp.costfct <= 2);
+      }
+    }
+    b0 = fold8(b0, 0.f, true, false);
+    if (NOP == 2) b1 = fold8(b1, 0.f, true, false);
+    sw = fold8(sw, 0.f, true, false);
+    if (active) {
+      if (finishing) {
+        active = false;
+      } else {
+        const float dpsq = (NOP == 2) ? dp0 * dp0 + dp1 * dp1 : dp0 * dp0;
+        if (cnt == 1) dpsq_init = dpsq;
+        mares_old = mares;
+        mares = sw / fn;
+        bool go = (cnt < pp.max_iter) & (mares > pp.res_thresh);
+        if (go && cnt >= pp.min_iter)
+          go = (dpsq / dpsq_init >= pp.dp_thresh_sq) & (mares / mares_old <= pp.dr_thresh);
+        if (!go) {
+          conv = 1;
+          active = false;
+        } else {
+          cnt++;
+          if (NOP == 2) {
+            const float y0 = b0 / L00;
+            const float y1 = (b1 - L10 * y0) / L11;
+            dp1 = y1 / L11;
+            dp0 = (y0 - L10 * dp1) / L00;
+            p0 = p0 - dp0;
+            p1 = p1 - dp1;
+            ptx = refx + p0;
+            pty = refy + p1;
+          } else {
+            dp0 = (b0 / L00) / L00;
+            p0 = p0 - dp0;
+            p0 = (camlr_of(g, frame) == 0) ? std_min(p0, 0.0f) : std_max(p0, 0.0f);
+            ptx = refx + p0;
+          }
+          const float ex = stx - ptx, ey = sty - pty;
+          if (sqrtf(ex * ex + ey * ey) > g.outlierthresh || ptx < g.lb || pty < g.lb || ptx > g.ubw ||
+              pty > g.ubh) {
+            p0 = pin0;
+            p1 = pin1;
+            ptx = refx + p0;
+            if (NOP == 2) pty = refy + p1;
+            conv = 1;
+            finishing = true;
+          }
+        }
+      }
+    }
+  }
+  if (valid) {
+    float* pw = g.pat_w + ((size_t)frame * g.np + ip) * Cfg::N;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) pw[l8 + 8 * k] = wrote_w ? fabsf(R[k]) : 0.f;
+    if (l8 == 0) {
+      float* po = g.pat_p + ((size_t)frame * g.np + ip) * NOP;
+      po[0] = p0;
+      if (NOP == 2) po[1] = p1;
+      g.pat_conv[(size_t)frame * g.np + ip] = conv;
+      g.pat_cnt[(size_t)frame * g.np + ip] = cnt;
+    }
+  }
+}
+
 // usefbcon, second loop of AggregateFlowDense (patchgrid.cpp:278-375) as a gather: the patches of
 // the complementary frame `cq`, at their displaced positions, add their NEGATED flow with bilinear
 // weights.  The reference's scatter visits patches in ascending ip and the pixels of a patch in
@@ -688,6 +980,25 @@ int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int
     const dim3 grid8((g.np + 31) / 32, f1 - f0);
     if (g.nop == 2) patch_p8c1_kernel<2><<<grid8, 256, 0, st>>>(g, pp, f0, init_from_coarser ? 1 : 0);
     else patch_p8c1_kernel<1><<<grid8, 256, 0, st>>>(g, pp, f0, init_from_coarser ? 1 : 0);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
+  if (g.P == 12 && g.pad >= 12 && (g.noc == 1 || g.noc == 3)) {  // window-staged specialisation (operating points 3 and 4)
+    const int threads12 = 256;
+    const dim3 grid12((g.np + threads12 / 8 - 1) / (threads12 / 8), f1 - f0);
+    const int init = init_from_coarser ? 1 : 0;
+#define OFDIS_P12(NOPv, Cv)                                                                                        \
+  do {                                                                                                             \
+    constexpr int WH = (NOPv == 2) ? PwCfg<Cv>::W : PwCfg<Cv>::P + 1;                                              \
+    const size_t sm = sizeof(float) * ((size_t)(threads12 / 8) * WH * PwCfg<Cv>::WC +                              \
+                                       (Cv == 1 ? 0 : (size_t)2 * PwCfg<Cv>::NK * threads12));                     \
+    if (sm > 48 * 1024) cudaFuncSetAttribute(patch_p12_kernel<NOPv, Cv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+    patch_p12_kernel<NOPv, Cv><<<grid12, threads12, sm, st>>>(g, pp, f0, init);                                    \
+  } while (0)
+    if (g.nop == 2 && g.noc == 1) OFDIS_P12(2, 1);
+    else if (g.nop == 2) OFDIS_P12(2, 3);
+    else if (g.noc == 1) OFDIS_P12(1, 1);
+    else OFDIS_P12(1, 3);
+#undef OFDIS_P12
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
   const int n = g.novals;

@@ -73,6 +73,40 @@ int main() {
     printf("FAIL: per-level classes differ from OFClass\n");
     return 1;
   }
+  // Forward-backward couple (oflow.cpp:162-170,191-215): two stand-alone grids joined by SetComplGrid
+  // must give the flow OFClass computes with usefbcon = 1 (one level, no refinement).
+  {
+    const int sl = 2, w2 = W >> sl, h2 = H >> sl;
+    std::vector<float> fb_ref((size_t)w2 * h2 * 2), fw((size_t)w2 * h2 * 2), bw((size_t)w2 * h2 * 2);
+    OFClass fbc(pa.data(), pax.data(), pay.data(), pb.data(), pbx.data(), pby.data(), P, fb_ref.data(), nullptr, W, H, sl, sl,
+                12, 12, 0.05f, 0.95f, 0.f, P, 0.4f, true, 0, 1, 1, false, 10.f, 10.f, 5.f, 1, 3, 1.6f, 0);
+    optparam op2;
+    FillOptParam(op2, 2, sl, sl, 12, 12, 0.05f, 0.95f, 0.f, P, 0.4f, true, 0, 1, 1, false, 10.f, 10.f, 5.f, 1, 3, 1.6f, 0);
+    camparam cpl, cpr;
+    FillCamParam(cpl, op2, W, H, sl, P, 0);
+    FillCamParam(cpr, op2, W, H, sl, P, 1);
+    PatGridClass gfw(&cpl, &cpr, &op2), gbw(&cpr, &cpl, &op2);
+    gfw.SetComplGrid(&gbw);
+    gbw.SetComplGrid(&gfw);
+    gfw.InitializeGrid(pa[sl], pax[sl], pay[sl]);
+    gfw.SetTargetImage(pb[sl], pbx[sl], pby[sl]);
+    gbw.InitializeGrid(pb[sl], pbx[sl], pby[sl]);
+    gbw.SetTargetImage(pa[sl], pax[sl], pay[sl]);
+    gfw.Optimize();
+    gbw.Optimize();
+    gfw.AggregateFlowDense(fw.data());
+    gbw.AggregateFlowDense(bw.data());
+    if (memcmp(fw.data(), fb_ref.data(), sizeof(float) * fw.size())) {
+      printf("FAIL: SetComplGrid couple differs from OFClass(usefbcon=1)\n");
+      return 1;
+    }
+    double sb = 0;
+    for (float v : bw) sb += fabs(v);
+    if (!(sb > 0) || gbw.GetQuePatchDis(0)[0] != gbw.GetRefPatchPos(0)[0] - gbw.GetQuePatchPos(0)[0]) {
+      printf("FAIL: backward grid of the couple is empty\n");
+      return 1;
+    }
+  }
   double s = 0;
   for (float v : ref) s += fabs(v);
   printf("ok: %zu flow values bitwise equal (mean |flow| %.4f)\n", ref.size(), s / ref.size());

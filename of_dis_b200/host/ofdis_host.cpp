@@ -287,13 +287,60 @@ PatGridClass::PatGridClass(const camparam* cpt_in, const camparam* cpo_in, const
   offw = (cpt->width - (nopw - 1) * steps) / 2;
   offh = (cpt->height - (noph - 1) * steps) / 2;
   nopatches = nopw * noph;
+  device_id = device;
   ctx = level_context(cpt, op, device);
 }
 
-PatGridClass::~PatGridClass() { ofdis_destroy(ctx); }
+PatGridClass::Couple::~Couple() { ofdis_destroy(ctx); }
 
-void PatGridClass::SetComplGrid(PatGridClass*) {
-  throw std::runtime_error("PatGridClass::SetComplGrid: the forward-backward merge runs inside the engine; use OFClass with usefbcon=1");
+PatGridClass::~PatGridClass() {
+  if (couple) {
+    couple->grid[role] = nullptr;
+    ctx = nullptr;  // owned by the couple
+  }
+  ofdis_destroy(ctx);
+}
+
+void PatGridClass::SetComplGrid(PatGridClass* cg) {
+  if (!cg || cg == this) throw std::runtime_error("PatGridClass::SetComplGrid: need the other grid");
+  if (couple) {
+    if (couple->grid[role ^ 1] == cg) return;  // second half of oflow.cpp:169-170
+    throw std::runtime_error("PatGridClass::SetComplGrid: this grid already has a complementary grid");
+  }
+  if (cg->couple) throw std::runtime_error("PatGridClass::SetComplGrid: the other grid already has a complementary grid");
+  // one engine context with both directions: this grid becomes the forward one
+  auto c = std::make_shared<Couple>();
+  ofdis_params p = to_params(*op, cpt->curr_lv, cpt->curr_lv);
+  p.usefbcon = 1;
+  check(ofdis_create(&c->ctx, device_id, nullptr, &p, op->nop, cpt->width << cpt->curr_lv, cpt->height << cpt->curr_lv,
+                     cpt->imgpadding, 1),
+        nullptr, "ofdis_create (forward-backward couple)");
+  ofdis_set_dp_thresh_sq(c->ctx, op->dp_thresh);
+  c->grid[0] = this;
+  c->grid[1] = cg;
+  for (PatGridClass* g : {this, cg}) {
+    ofdis_destroy(g->ctx);  // the stand-alone one-direction context
+    g->ctx = c->ctx;
+    g->couple = c;
+    g->fetched = false;
+  }
+  role = 0;
+  cg->role = 1;
+}
+
+void PatGridClass::select() const {
+  if (couple) check(ofdis_set_direction(ctx, role), ctx, "ofdis_set_direction");
+}
+
+void PatGridClass::flush() {
+  if (!couple || couple->uploaded) return;
+  PatGridClass *f = couple->grid[0], *b = couple->grid[1];
+  if (!f || !b || !f->i0 || !b->i0 || !f->tgt || !b->tgt)
+    throw std::runtime_error("PatGridClass: both grids of a couple need InitializeGrid and SetTargetImage first");
+  // forward: template = its own image, target = the other grid's template (oflow.cpp:191-197)
+  check(ofdis_upload_level_fb(ctx, 0, cpt->curr_lv, f->i0, f->i0x, f->i0y, b->i0, b->i0x, b->i0y, OFDIS_MEM_HOST), ctx,
+        "ofdis_upload_level_fb");
+  couple->uploaded = true;
 }
 
 void PatGridClass::InitializeGrid(const float* a, const float* ax, const float* ay) {
@@ -302,25 +349,35 @@ void PatGridClass::InitializeGrid(const float* a, const float* ax, const float* 
   i0y = ay;
   from_coarser = false;  // p_init reset (patchgrid.cpp:113)
   fetched = false;
+  if (couple) couple->uploaded = false;
 }
 
 void PatGridClass::SetTargetImage(const float* b, const float*, const float*) {
   if (!i0) throw std::runtime_error("PatGridClass::SetTargetImage before InitializeGrid");
-  check(ofdis_upload_level(ctx, 0, cpt->curr_lv, i0, i0x, i0y, b, OFDIS_MEM_HOST), ctx, "ofdis_upload_level");
+  tgt = b;
+  if (couple) {
+    couple->uploaded = false;
+  } else {
+    check(ofdis_upload_level(ctx, 0, cpt->curr_lv, i0, i0x, i0y, b, OFDIS_MEM_HOST), ctx, "ofdis_upload_level");
+  }
   fetched = false;
 }
 
 void PatGridClass::InitializeFromCoarserOF(const float* flow_prev) {
+  select();
   check(ofdis_set_flow(ctx, 0, cpt->curr_lv + 1, flow_prev, OFDIS_MEM_HOST), ctx, "ofdis_set_flow");
   from_coarser = true;
 }
 
 void PatGridClass::Optimize() {
+  flush();
+  select();
   check(ofdis_patgrid_optimize(ctx, cpt->curr_lv, 0, 1, from_coarser ? 1 : 0), ctx, "ofdis_patgrid_optimize");
   fetched = false;
 }
 
 void PatGridClass::AggregateFlowDense(float* flowout) const {
+  select();
   check(ofdis_patgrid_aggregate(ctx, cpt->curr_lv, 0, 1), ctx, "ofdis_patgrid_aggregate");
   check(ofdis_get_flow(ctx, 0, cpt->curr_lv, flowout, OFDIS_MEM_HOST), ctx, "ofdis_get_flow");
 }
@@ -328,6 +385,7 @@ void PatGridClass::AggregateFlowDense(float* flowout) const {
 void PatGridClass::fetch() const {
   if (fetched) return;
   p_host.resize((size_t)nopatches * op->nop);
+  select();
   check(ofdis_get_patches(ctx, 0, cpt->curr_lv, p_host.data(), nullptr, nullptr, nullptr), ctx, "ofdis_get_patches");
   fetched = true;
 }

@@ -11,6 +11,7 @@
 #ifndef OFDIS_HOST_H
 #define OFDIS_HOST_H
 
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -97,7 +98,10 @@ class PatGridClass {
   void InitializeFromCoarserOF(const float* flow_prev);
   void AggregateFlowDense(float* flowout) const;
   void Optimize();
-  void SetComplGrid(PatGridClass* cg_in);  // throws: the merge runs inside the engine (OFClass, usefbcon=1)
+  // patchgrid.h:36: joins this grid and `cg_in` (the grid on the swapped images) so that
+  // AggregateFlowDense merges the complementary grid's flow (patchgrid.cpp:278-375).  Both grids
+  // then live in one two-direction engine context; call it on both objects like oflow.cpp:166-170.
+  void SetComplGrid(PatGridClass* cg_in);
   inline int GetNoPatches() const { return nopatches; }
   inline int GetNoph() const { return noph; }
   inline int GetNopw() const { return nopw; }
@@ -107,6 +111,18 @@ class PatGridClass {
 
  private:
   void fetch() const;
+  void select() const;   // couple: address this grid's direction in the shared context
+  void flush();          // couple: upload both grids' images once both are bound
+  struct Couple {         // two grids joined by SetComplGrid share one usefbcon context
+    ofdis_ctx* ctx = nullptr;
+    PatGridClass* grid[2] = {nullptr, nullptr};
+    bool uploaded = false;
+    ~Couple();
+  };
+  std::shared_ptr<Couple> couple;
+  int role = 0;          // 0 = forward grid of the couple, 1 = backward
+  const float *tgt = nullptr;
+  int device_id = 0;
   const camparam* cpt;
   const optparam* op;
   ofdis_ctx* ctx = nullptr;

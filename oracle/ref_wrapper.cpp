@@ -217,64 +217,86 @@ inline int refl(int v, int n) {
   while (v < 0 || v >= n) v = v < 0 ? -v : 2 * (n - 1) - v;
   return v;
 }
-Img border(const Img& s, int pad, bool replicate) {  // copyMakeBorder (run_dense.cpp:163-172)
-  Img d;
+// all outputs are resized in place: a worker thread reuses its buffers from pair to pair
+void border(const Img& s, int pad, bool replicate, Img& d) {  // copyMakeBorder (run_dense.cpp:163-172)
   d.w = s.w + 2 * pad; d.h = s.h + 2 * pad; d.c = s.c;
   d.px.assign((size_t)d.w * d.h * d.c, 0.f);
-  for (int y = 0; y < d.h; ++y)
-    for (int x = 0; x < d.w; ++x) {
-      const int sx = x - pad, sy = y - pad;
-      if (!replicate && (sx < 0 || sy < 0 || sx >= s.w || sy >= s.h)) continue;
-      for (int k = 0; k < s.c; ++k) d.at(x, y, k) = s.at(clampi(sx, s.w), clampi(sy, s.h), k);
-    }
-  return d;
+  const int rowf = s.w * s.c;
+  for (int y = 0; y < d.h; ++y) {
+    const int sy = y - pad;
+    if (!replicate && (sy < 0 || sy >= s.h)) continue;
+    const float* src = &s.px[(size_t)clampi(sy, s.h) * rowf];
+    float* dst = &d.px[(size_t)y * d.w * d.c];
+    std::memcpy(dst + (size_t)pad * s.c, src, sizeof(float) * rowf);
+    if (replicate)
+      for (int x = 0; x < pad; ++x)
+        for (int k = 0; k < s.c; ++k) {
+          dst[x * s.c + k] = src[k];
+          dst[(size_t)(pad + s.w + x) * s.c + k] = src[(size_t)(s.w - 1) * s.c + k];
+        }
+  }
 }
-Img half(const Img& s) {  // cv::resize(.5,.5) on even sizes (run_dense.cpp:150)
-  Img d;
+void half(const Img& s, Img& d) {  // cv::resize(.5,.5) on even sizes (run_dense.cpp:150)
   d.w = s.w / 2; d.h = s.h / 2; d.c = s.c;
   d.px.resize((size_t)d.w * d.h * d.c);
   for (int y = 0; y < d.h; ++y)
     for (int x = 0; x < d.w; ++x)
       for (int k = 0; k < s.c; ++k)
         d.at(x, y, k) = ((s.at(2 * x, 2 * y, k) + s.at(2 * x + 1, 2 * y, k)) + (s.at(2 * x, 2 * y + 1, k) + s.at(2 * x + 1, 2 * y + 1, k))) * 0.25f;
-  return d;
 }
 void sobel(const Img& s, Img& dx, Img& dy) {  // cv::Sobel 3x3, scale 1/8 (run_dense.cpp:156-157)
-  dx = s; dy = s;
-  for (int y = 0; y < s.h; ++y)
-    for (int x = 0; x < s.w; ++x)
-      for (int k = 0; k < s.c; ++k) {
-        const int xm = refl(x - 1, s.w), xp = refl(x + 1, s.w), ym = refl(y - 1, s.h), yp = refl(y + 1, s.h);
-        const float t0 = s.at(xp, ym, k) - s.at(xm, ym, k), t1 = s.at(xp, y, k) - s.at(xm, y, k), t2 = s.at(xp, yp, k) - s.at(xm, yp, k);
-        dx.at(x, y, k) = (t0 * 0.125f + t1 * 0.25f) + t2 * 0.125f;
-        const float s0 = (s.at(xm, ym, k) * 0.125f + s.at(x, ym, k) * 0.25f) + s.at(xp, ym, k) * 0.125f;
-        const float s2 = (s.at(xm, yp, k) * 0.125f + s.at(x, yp, k) * 0.25f) + s.at(xp, yp, k) * 0.125f;
-        dy.at(x, y, k) = s2 - s0;
+  dx.w = dy.w = s.w; dx.h = dy.h = s.h; dx.c = dy.c = s.c;
+  dx.px.resize(s.px.size());
+  dy.px.resize(s.px.size());
+  const int c = s.c;
+  for (int y = 0; y < s.h; ++y) {
+    const float* rm = &s.px[(size_t)refl(y - 1, s.h) * s.w * c];
+    const float* r0 = &s.px[(size_t)y * s.w * c];
+    const float* rp = &s.px[(size_t)refl(y + 1, s.h) * s.w * c];
+    float* ox = &dx.px[(size_t)y * s.w * c];
+    float* oy = &dy.px[(size_t)y * s.w * c];
+    for (int x = 0; x < s.w; ++x) {
+      const int xm = refl(x - 1, s.w) * c, xp = refl(x + 1, s.w) * c, x0 = x * c;
+      for (int k = 0; k < c; ++k) {
+        const float t0 = rm[xp + k] - rm[xm + k], t1 = r0[xp + k] - r0[xm + k], t2 = rp[xp + k] - rp[xm + k];
+        ox[x0 + k] = (t0 * 0.125f + t1 * 0.25f) + t2 * 0.125f;
+        const float s0 = (rm[xm + k] * 0.125f + rm[x0 + k] * 0.25f) + rm[xp + k] * 0.125f;
+        const float s2 = (rp[xm + k] * 0.125f + rp[x0 + k] * 0.25f) + rp[xp + k] * 0.125f;
+        oy[x0 + k] = s2 - s0;
       }
+    }
+  }
 }
 struct Pyr {
-  std::vector<Img> im, dx, dy;
+  std::vector<Img> raw, rdx, rdy, im, dx, dy;
   std::vector<const float*> pim, pdx, pdy;
   void build(const unsigned char* u8, int w_org, int h_org, int c, int W, int H, int lv_f, int pad) {
+    const size_t n = lv_f + 1;
+    if (raw.size() != n) {
+      raw.resize(n); rdx.resize(n); rdy.resize(n); im.resize(n); dx.resize(n); dy.resize(n);
+      pim.resize(n); pdx.resize(n); pdy.resize(n);
+    }
     // divisibility padding: replicate, floor(pad/2) left/top (run_dense.cpp:298-311), then float
-    Img base;
+    Img& base = raw[0];
     base.w = W; base.h = H; base.c = c;
     base.px.resize((size_t)W * H * c);
     const int pl = (W - w_org) / 2, pt = (H - h_org) / 2;
-    for (int y = 0; y < H; ++y)
-      for (int x = 0; x < W; ++x)
-        for (int k = 0; k < c; ++k)
-          base.at(x, y, k) = (float)u8[((size_t)clampi(y - pt, h_org) * w_org + clampi(x - pl, w_org)) * c + k];
-    im.resize(lv_f + 1); dx.resize(lv_f + 1); dy.resize(lv_f + 1);
-    pim.resize(lv_f + 1); pdx.resize(lv_f + 1); pdy.resize(lv_f + 1);
-    for (int i = 0; i <= lv_f; ++i) {
-      im[i] = i == 0 ? base : half(im[i - 1]);
-      sobel(im[i], dx[i], dy[i]);
+    for (int y = 0; y < H; ++y) {
+      const unsigned char* src = u8 + (size_t)clampi(y - pt, h_org) * w_org * c;
+      float* dst = &base.px[(size_t)y * W * c];
+      for (int x = 0; x < W; ++x) {
+        const int sx = clampi(x - pl, w_org) * c;
+        for (int k = 0; k < c; ++k) dst[x * c + k] = (float)src[sx + k];
+      }
     }
-    for (int i = 0; i <= lv_f; ++i) {
-      im[i] = border(im[i], pad, true);
-      dx[i] = border(dx[i], pad, false);
-      dy[i] = border(dy[i], pad, false);
+    for (size_t i = 0; i < n; ++i) {
+      if (i > 0) half(raw[i - 1], raw[i]);
+      sobel(raw[i], rdx[i], rdy[i]);
+    }
+    for (size_t i = 0; i < n; ++i) {
+      border(raw[i], pad, true, im[i]);
+      border(rdx[i], pad, false, dx[i]);
+      border(rdy[i], pad, false, dy[i]);
       pim[i] = im[i].px.data(); pdx[i] = dx[i].px.data(); pdy[i] = dy[i].px.data();
     }
   }
@@ -323,13 +345,14 @@ double ofdis_ref_run_many_u8(const unsigned char* frames, int npairs, int nrep, 
   std::vector<std::thread> pool;
   for (int t = 0; t < threads; ++t)
     pool.emplace_back([&]() {
+      Pyr A, B;  // per-thread buffers, reused from pair to pair
+      std::vector<float> fl;
       for (long i = next.fetch_add(1); i < total; i = next.fetch_add(1)) {
         const int q = (int)(i % npairs);
-        Pyr A, B;
         A.build(frames + (size_t)q * 2 * img, w_org, h_org, c, W, H, p->sc_f, p->p_samp_s);
         B.build(frames + (size_t)q * 2 * img + img, w_org, h_org, c, W, H, p->sc_f, p->p_samp_s);
         const int w = W >> p->sc_l, h = H >> p->sc_l;
-        std::vector<float> fl((size_t)w * h * nop);
+        fl.resize((size_t)w * h * nop);
         ofdis_ref_run(A.pim.data(), A.pdx.data(), A.pdy.data(), B.pim.data(), B.pdx.data(), B.pdy.data(), p->p_samp_s,
                       fl.data(), nullptr, W, H, p);
         upsample_crop(fl.data(), w, h, nop, 1 << p->sc_l, w_org, h_org, W, H, out + (size_t)q * w_org * h_org * nop);

@@ -104,3 +104,61 @@ def test_properties_zero_flow_and_translation(oracle_port):
     fl = preprocess.postprocess(oracle_port.port_run(pyr, prm), prm.sc_l, pyr.padw, pyr.padh, 192, 128)
     inner = fl[16:-16, 16:-16]
     assert abs(np.median(inner[..., 0]) - 2.0) < 0.1 and abs(np.median(inner[..., 1])) < 0.1
+
+
+# ---- the port against the reference build on everything the GPU tests use it for ----------------
+@pytest.mark.skipif(not ref_driver.ref_available("m1c1"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", range(40))
+def test_port_vs_reference_on_the_random_configurations_of_the_gpu_suite(seed, oracle_port):
+    """The 40 seeded parameter sets of tests/test_gpu_parity.py::test_random_configurations_vs_oracle:
+    the port (the GPU tests' checker) must equal the reference build on each of them."""
+    from test_gpu_parity import _random_config
+
+    rng = np.random.default_rng(1000 + seed)
+    numbers, ch, nop, size, amp = _random_config(rng)
+    prm = params.from_cli_numbers(numbers, noc=ch, nop=nop)
+    if not ref_driver.ref_available(prm.flavour()):
+        pytest.skip("flavour not built")
+    i0, i1, _ = synth.synthetic_pair(size[0], size[1], ch, seed=200 + seed, stereo=(nop == 1), amp=amp)
+    pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
+    assert np.array_equal(bits(ref_driver.ref_run(pyr, prm)), bits(oracle_port.port_run(pyr, prm)))
+
+
+BASELINE_CASES = {
+    "cfg2_seed1": (436, 1024, 1, lambda: params.operating_point(2, 1024), 1, False),
+    "cfg2_seed7": (436, 1024, 1, lambda: params.operating_point(2, 1024), 7, False),
+    "cfg3_1920x1080_rgb_l1": (1080, 1920, 3, lambda: params.from_cli_numbers(
+        "6 2 16 16 0.05 0.95 0 12 0.75 0 1 1 1 10 10 5 1 3 1.6 0".split(), noc=3), 2, False),
+    "cfg5_2880x1988_stereo_op4": (1988, 2880, 1, lambda: params.operating_point(4, 2880, noc=1, nop=1), 4, True),
+}
+
+
+@pytest.mark.skipif(not ref_driver.ref_available("m1c1"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", list(BASELINE_CASES))
+def test_port_vs_reference_at_baseline_sizes(name, oracle_port):
+    """BASELINE configs[1], [2] and [4] at full size (the inputs of the GPU suite's full-size tests)."""
+    h, w, ch, mk, seed, stereo = BASELINE_CASES[name]
+    prm = mk()
+    if not ref_driver.ref_available(prm.flavour()):
+        pytest.skip("flavour not built")
+    i0, i1, _ = synth.synthetic_pair(h, w, ch, seed=seed, stereo=stereo, amp=6.0)
+    pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
+    assert np.array_equal(bits(ref_driver.ref_run(pyr, prm)), bits(oracle_port.port_run(pyr, prm)))
+
+
+@pytest.mark.skipif(not ref_driver.ref_available("m1c1"), reason="oracle/_ref not built")
+def test_native_thread_pool_drivers_reproduce_single_runs():
+    """ofdis_ref_run_many / ofdis_ref_run_many_u8 (the CPU baseline's drivers): same flows as one
+    ofdis_ref_run per pair, and the restated pyramid / upsampling equal of_dis_b200/preprocess.py
+    (which tests/test_preprocess.py pins to cv2), bit for bit."""
+    prm = params.from_cli_numbers("3 1 8 8 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split())
+    pairs = [synth.synthetic_pair(121, 203, 1, seed=30 + s)[:2] for s in range(3)]  # odd size: padding + crop
+    pyrs = [preprocess.PairPyramids(a, b, prm.sc_f, prm.p_samp_s) for a, b in pairs]
+    _, flows = ref_driver.ref_run_many(pyrs, prm, nrep=2, threads=3)
+    frames = np.stack([np.stack([a, b]) for a, b in pairs])[..., None]
+    _, full = ref_driver.ref_run_many_u8(frames, prm, nrep=1, threads=2)
+    for q, p in enumerate(pyrs):
+        one = ref_driver.ref_run(p, prm)
+        assert np.array_equal(bits(flows[q]), bits(one))
+        exp = preprocess.postprocess(one, prm.sc_l, p.padw, p.padh, 203, 121)
+        assert np.array_equal(bits(full[q]), bits(exp.reshape(full[q].shape)))

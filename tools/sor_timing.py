@@ -16,10 +16,10 @@ ctx.run(8)
 ctx.sync()
 buf = np.zeros(64 * 8 * 16, np.int64)
 assert api.lib().ofdis_debug_sor_times(buf.ctypes.data_as(ctypes.c_void_p)) == 0
-t = buf.reshape(64, 8, 16)[:6, :, :7]   # last launch = level 3 (6 warps), steps 40..47
+t = buf.reshape(64, 8, 16)[:7, :, :7]   # last launch = level 3 (6 compute warps + the producer), steps 40..47
 names = ["start", "mbarwait", "lds", "prep", "chain", "stores", "barrier"]
-for wp in range(6):
+for wp in range(7):
     d = np.diff(t[wp], axis=1)          # per-step phase durations
-    nxt = t[wp, 1:, 0] - t[wp, :-1, 6]  # barrier exit -> next start
-    print("warp %d (k=%d rows %d..): mean cycles per phase %s | step total %.0f" %
-          (wp, wp // 2, 32 * (wp % 2), dict(zip(names[1:], d.mean(0).round(0))), (t[wp, 1:, 0] - t[wp, :-1, 0]).mean()))
+    role = "producer (issue, -, stage wait, -, -, halo wait, barrier)" if wp == 6 else "k=%d rows %d.." % (wp // 2, 32 * (wp % 2))
+    print("warp %d %s: mean cycles per phase %s | step total %.0f" %
+          (wp, role, dict(zip(names[1:], d.mean(0).round(0))), (t[wp, 1:, 0] - t[wp, :-1, 0]).mean()))
