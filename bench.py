@@ -333,6 +333,8 @@ def main():
                          "them (default: the region the reference arm times), finest = un-padded I0,I1 of the finest used "
                          "level, images = padded I0,I1 of every level, cli = 8-bit frames in / full-resolution flow out")
     ap.add_argument("--no-extras", action="store_true", help="skip the sharded and big_configs legs")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="ofdis_set_option on every context (launch-geometry experiments; results are bit-identical)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.lanes <= 0:
@@ -360,6 +362,17 @@ def main():
     # a non-default torch stream: the context enqueues on it and torch.cuda.Event times it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
+    opts = dict((o.split("=")[0], int(o.split("=")[1])) for o in args.opt)
+    if opts:  # every context created below gets the options
+        _Context = api.Context
+
+        def _ctx_with_opts(*a, **k):
+            c = _Context(*a, **k)
+            for name, val in opts.items():
+                c.set_option(name, val)
+            return c
+
+        api.Context = _ctx_with_opts
     ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, B, device=local,
                       stream=stream.cuda_stream)
     ff = ctx.packed_frame_floats

@@ -69,7 +69,7 @@ enum {
   OFDIS_OK = 0,
   OFDIS_ERR_ARG = -1,         /* bad argument / unsupported geometry */
   OFDIS_ERR_CUDA = -2,        /* a CUDA call failed; see ofdis_last_error */
-  OFDIS_ERR_UNSUPPORTED = -3, /* valid in the reference but not built here (refinement levels taller than 256 rows x the largest thread-block cluster, i.e. 2048 or 4096 rows; ofdis_upload_packed with usefbcon) */
+  OFDIS_ERR_UNSUPPORTED = -3, /* valid in the reference but not built here (refinement levels taller than ~256 rows x the largest thread-block cluster -- the SOR's shared-memory ring bounds the rows of one band --, i.e. 2048 rows, 4096 where the device grants 16-CTA clusters; ofdis_upload_packed with usefbcon) */
   OFDIS_ERR_NOMEM = -4
 };
 enum { OFDIS_MEM_HOST = 0, OFDIS_MEM_DEVICE = 1 };
@@ -193,9 +193,11 @@ int ofdis_profile_levels(ofdis_ctx* ctx, int nframes, int steps, double* ms_by_c
  * (patchgrid.h:36, oflow.cpp:162-170) are built on. */
 int ofdis_set_direction(ofdis_ctx* ctx, int dir);
 /* Launch-geometry options (tuning / test hook, results are bit-identical under every setting):
- *   "sor_single_max"  32 | 64 | 128 (default): refinement levels of up to this many rows run their SOR in
- *                     one CTA, taller ones in a thread-block cluster of row bands (sor_wave_kernel.cuh)
- *   "sor_max_cluster" 8 (portable, default unless the finest level needs more) | 16 */
+ *   "sor_rows_per_thread" 1 (default for flow) | 2 (default for stereo) | 4: rows of the 4-column tile one SOR thread updates per super-step
+ *                     (a level needs W/4 + h/rows super-steps; sor_wave_kernel.cuh)
+ *   "sor_single_max"  32 | 64 | 128 (default): refinement levels of up to this many SOR lanes (= rows / rows per
+ *                     thread) run their SOR in one CTA, taller ones in a thread-block cluster of row bands
+ *   "sor_max_cluster" 8 (portable) | 16 (default where the device grants it) */
 int ofdis_set_option(ofdis_ctx* ctx, const char* name, int value);
 /* CUDA-graph replay of ofdis_run (captured on first use per nframes). */
 int ofdis_set_graph_mode(ofdis_ctx* ctx, int enabled);

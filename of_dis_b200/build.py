@@ -44,8 +44,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     extra = ["-DOFDIS_SOR_TIMING"] if os.environ.get("OFDIS_SOR_TIMING") else []
+    extra += ["-D" + d for d in os.environ.get("OFDIS_EXP_DEFINES", "").split()]  # experiment builds of tools/ only
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-o", LIB]  # -ldl: NVTX v3 loads its injection library lazily
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode:
         sys.stderr.write(res.stdout + res.stderr)
@@ -73,6 +74,7 @@ def build_host(force: bool = False) -> str:
     for name, (m, c) in CLI_TARGETS.items():  # batch front-end: list file in, many pairs per launch
         jobs[name + "_batch"] = jobs[name] + ["-DOFDIS_BATCH"]
     jobs["ofdis_host_selftest"] = common + [os.path.join(HOST, "host_selftest.cpp")]
+    jobs["ofdis_imgdump"] = common + [os.path.join(HOST, "run_dense.cpp"), "-DOFDIS_IMGDUMP"]  # decoder test tool (no GPU)
     for name, cmd in jobs.items():
         out = os.path.join(BINDIR, name)
         if force or not os.path.exists(out) or os.path.getmtime(out) < newest:

@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/ofdis_b200.h"
 #include "ofdis_internal.cuh"
 
@@ -29,7 +31,7 @@ struct ofdis_ctx {
   int sel_dir = -1;                // ofdis_set_direction: -1 = both directions / the forward grid
   // SOR band plan (sor_band_plan): levels of up to sor_single_max rows run in one CTA, taller ones in a
   // cluster of up to sor_max_cluster CTAs (8 = portable limit; 16 where the device grants it)
-  int sor_single_max = 128, sor_max_cluster = 8, sor_dev_cluster = 8;
+  int sor_single_max = 128, sor_max_cluster = 8, sor_dev_cluster = 8, sor_rt = 1;  // defaults set in ofdis_create
   int nlev = 0;                    // sc_f - sc_l + 1
   std::vector<LevelGeom> lev;      // index: level - sc_l
   std::vector<size_t> img_off;     // [lev][4] offsets (floats) inside one packed frame
@@ -57,6 +59,18 @@ struct ofdis_ctx {
 };
 
 namespace {
+
+// NVTX range per stage and level ("patch L3", "densify L3", "varref L3", "pyramid", "upsample"): free
+// when no profiler is attached, names the stages in Nsight Systems / ncu --nvtx timelines.
+struct NvtxRange {
+  NvtxRange(const char* stage, int level) {
+    char name[48];
+    if (level >= 0) snprintf(name, sizeof(name), "ofdis %s L%d", stage, level);
+    else snprintf(name, sizeof(name), "ofdis %s", stage);
+    nvtxRangePushA(name);
+  }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 int fail(ofdis_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
   if (c) {
@@ -164,7 +178,7 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
   if (prm->usetvref && ((height >> prm->sc_f) < 4 || (width >> prm->sc_f) < 2)) return OFDIS_ERR_ARG;  // image.c:401-434 needs >= 4 rows
   if (prm->usetvref) {  // tallest refinement level: 256-row bands x a cluster of 16 CTAs at most (re-checked for the device below)
     VarRefPlanes probe{};
-    if (!sor_band_plan(width >> prm->sc_l, height >> prm->sc_l, 128, 16, &probe)) return OFDIS_ERR_UNSUPPORTED;
+    if (!sor_band_plan(width >> prm->sc_l, height >> prm->sc_l, 4, 128, 16, nop, 1, &probe)) return OFDIS_ERR_UNSUPPORTED;
   }
 
   ofdis_ctx* ctx = new (std::nothrow) ofdis_ctx();
@@ -195,14 +209,17 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
     ctx->own_stream = true;
   }
   if (prm->usetvref) {  // tallest refinement level: 256-row bands x the largest cluster the device grants
+    // Measured defaults (tools/big_configs.py, bench.py --opt): the largest cluster the device grants
+    // (16 CTAs: -10..20 % on levels of 272..1024 rows against 8); two rows per SOR thread for stereo
+    // (-23 % on configs[4]), one for flow (two rows: -3 % on configs[2], +4 % on the 56-row bench level).
     ctx->sor_dev_cluster = sor_max_cluster_size();
+    ctx->sor_max_cluster = ctx->sor_dev_cluster;
+    ctx->sor_rt = (nop == 1) ? 2 : 1;
     VarRefPlanes probe{};
-    if (!sor_band_plan(width >> prm->sc_l, height >> prm->sc_l, 128, 8, &probe)) {
-      if (!sor_band_plan(width >> prm->sc_l, height >> prm->sc_l, 128, ctx->sor_dev_cluster, &probe)) {
-        ofdis_destroy(ctx);
-        return OFDIS_ERR_UNSUPPORTED;
-      }
-      ctx->sor_max_cluster = ctx->sor_dev_cluster;
+    const int fw = width >> prm->sc_l, fh = height >> prm->sc_l;
+    if (!sor_band_plan(fw, fh, ctx->sor_rt, 128, ctx->sor_max_cluster, nop, prm->tv_solverit, &probe)) {
+      ofdis_destroy(ctx);
+      return OFDIS_ERR_UNSUPPORTED;
     }
   }
   ctx->pp.max_iter = prm->max_iter;
@@ -282,15 +299,16 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
     const LevelGeom& Lf = ctx->lev[0];
     const size_t plane = (size_t)Lf.pitch * Lf.h;
     const int C = prm->noc;
-    // band-skewed SOR arrays: nb bands x (W4 + hpad + 2) diagonals x hpad rows, 8 (rec) + 2 (dudv)
-    // float4 per block; sized for the largest level under either cluster limit
+    // band-skewed SOR arrays: nb bands x (W4 + hpad + 2) diagonals x rt rows x hpad lanes, 8 (rec) + 2
+    // (dudv) float4 per block; sized for the largest level under every plan ofdis_set_option can select
     size_t diag = 0;
     for (const LevelGeom& L : ctx->lev)
       for (int mc = 8; mc <= ctx->sor_dev_cluster; mc += 8)
-        for (int sm = 32; sm <= 128; sm *= 2) {  // every plan ofdis_set_option can select
-          VarRefPlanes t{};
-          if (sor_band_plan(L.w, L.h, sm, mc, &t)) diag = std::max(diag, (size_t)t.nb * t.ndiag * t.hpad);
-        }
+        for (int sm = 32; sm <= 128; sm *= 2)
+          for (int rt = 1; rt <= 4; rt *= 2) {
+            VarRefPlanes t{};
+            if (sor_band_plan(L.w, L.h, rt, sm, mc, nop, prm->tv_solverit, &t)) diag = std::max(diag, (size_t)t.nb * t.ndiag * t.rt * t.hpad);
+          }
     const size_t per_frame = plane * (1 + C + 8 * C) + diag * 4 * (8 + 2);
     ok = dalloc((void**)&ctx->d_planes, sizeof(float) * per_frame * cap);
     if (ok) {
@@ -467,6 +485,7 @@ int ofdis_upload_packed_images(ofdis_ctx* ctx, int f0, int f1, const float* pack
 
 // Coarser levels by 2x2 box means (forward frames), then finish_gradients.
 static int finish_pyramid(ofdis_ctx* ctx, int f0, int f1) {
+  NvtxRange nvtx("pyramid", -1);
   const int D = ctx->dirs, q0 = f0 * D, nq = f1 - f0;
   for (int sl = ctx->prm.sc_l + 1; sl <= ctx->prm.sc_f; ++sl) {
     const LevelGeom gs = stepped(ctx->lev[sl - 1 - ctx->prm.sc_l], D), gd = stepped(ctx->lev[sl - ctx->prm.sc_l], D);
@@ -553,6 +572,7 @@ int ofdis_get_flow_fullres(ofdis_ctx* ctx, int f0, int f1, float* out, int width
   int cx, cy;
   int rc = org_padding(ctx, width_org, height_org, &cx, &cy);
   if (rc) return rc;
+  NvtxRange nvtx("upsample", -1);
   CK(cudaSetDevice(ctx->device));
   const size_t per = (size_t)width_org * height_org * ctx->nop;
   float* dst = out;
@@ -584,6 +604,7 @@ int ofdis_patgrid_optimize(ofdis_ctx* ctx, int level, int f0, int f1, int init_f
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_optimize: bad argument");
   CK(cudaSetDevice(ctx->device));
   if (ctx->sel_dir >= 0 && f1 != f0 + 1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_optimize: one frame at a time while a direction is selected");
+  NvtxRange nvtx("patch", level);
   const int q0 = ctx->sel_dir >= 0 ? f0 * ctx->dirs + ctx->sel_dir : f0 * ctx->dirs;
   const int q1 = ctx->sel_dir >= 0 ? q0 + 1 : f1 * ctx->dirs;
   const int n = launch_patch_optimize(*L, ctx->pp, q0, q1, init_from_coarser != 0, ctx->stream, ctx->prof);
@@ -597,6 +618,7 @@ int ofdis_patgrid_aggregate(ofdis_ctx* ctx, int level, int f0, int f1) {
   LevelGeom* L = level_of(ctx, level);
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_aggregate: bad argument");
   CK(cudaSetDevice(ctx->device));
+  NvtxRange nvtx("densify", level);
   int n;
   if (ctx->dirs == 2) {
     // both grids' patch positions first; the backward flow is not densified on the last level (oflow.cpp:269-270)
@@ -621,6 +643,7 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "varref_refine: bad argument");
   if (!ctx->d_planes) return fail(ctx, OFDIS_ERR_ARG, "varref_refine: context created with usetvref=0");
   CK(cudaSetDevice(ctx->device));
+  NvtxRange nvtx("varref", level);
   VarRefParams vp;
   // refine_variational.cpp:36-43
   vp.n_inner = n_inner_override >= 0 ? n_inner_override : ctx->prm.tv_innerit * (level + 1);
@@ -631,10 +654,10 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   vp.half_delta_over3 = ctx->prm.tv_delta * 0.5f / 3.0f;
   VarRefPlanes pl = ctx->planes;
   pl.plane = (size_t)L->pitch * L->h;
-  if (!sor_band_plan(L->w, L->h, ctx->sor_single_max, ctx->sor_max_cluster, &pl))
+  if (!sor_band_plan(L->w, L->h, ctx->sor_rt, ctx->sor_single_max, ctx->sor_max_cluster, ctx->nop, ctx->prm.tv_solverit, &pl))
     return fail(ctx, OFDIS_ERR_UNSUPPORTED, "varref_refine: level too tall for the largest SOR cluster");
   {
-    const size_t diag = (size_t)pl.nb * pl.ndiag * pl.hpad;
+    const size_t diag = (size_t)pl.nb * pl.ndiag * pl.rt * pl.hpad;
     pl.rec_stride = diag * (L->nop == 2 ? 8 : 5);
     pl.dudv_stride = diag * 2;
   }
@@ -672,9 +695,15 @@ int ofdis_set_option(ofdis_ctx* ctx, const char* name, int value) {
     if (value != 8 && value != 16) return fail(ctx, OFDIS_ERR_ARG, "sor_max_cluster: 8 or 16");
     if (value > ctx->sor_dev_cluster) return fail(ctx, OFDIS_ERR_UNSUPPORTED, "sor_max_cluster: the device does not grant clusters of 16 CTAs");
     VarRefPlanes probe{};
-    if (ctx->prm.usetvref && !sor_band_plan(ctx->lev[0].w, ctx->lev[0].h, 128, value, &probe))
+    if (ctx->prm.usetvref && !sor_band_plan(ctx->lev[0].w, ctx->lev[0].h, ctx->sor_rt, 128, value, ctx->nop, ctx->prm.tv_solverit, &probe))
       return fail(ctx, OFDIS_ERR_UNSUPPORTED, "sor_max_cluster: the finest level needs the larger cluster");
     ctx->sor_max_cluster = value;
+  } else if (!strcmp(name, "sor_rows_per_thread")) {
+    if (value != 1 && value != 2 && value != 4) return fail(ctx, OFDIS_ERR_ARG, "sor_rows_per_thread: 1, 2 or 4");
+    VarRefPlanes probe{};
+    if (ctx->prm.usetvref && !sor_band_plan(ctx->lev[0].w, ctx->lev[0].h, value, 128, ctx->sor_max_cluster, ctx->nop, ctx->prm.tv_solverit, &probe))
+      return fail(ctx, OFDIS_ERR_UNSUPPORTED, "sor_rows_per_thread: the finest level needs more rows per thread or the larger cluster");
+    ctx->sor_rt = value;
   } else {
     return fail(ctx, OFDIS_ERR_ARG, "set_option: unknown option");
   }
@@ -693,6 +722,7 @@ int ofdis_run(ofdis_ctx* ctx, int nframes, int use_initflow) {
   if (!ctx) return OFDIS_ERR_ARG;
   if (nframes < 1 || nframes > ctx->max_frames) return fail(ctx, OFDIS_ERR_ARG, "run: bad frame count");
   CK(cudaSetDevice(ctx->device));
+  NvtxRange nvtx(ctx->graph_mode ? "run (graph)" : "run", -1);
   if (!ctx->graph_mode) return run_levels(ctx, nframes, use_initflow);
   const long key = (long)nframes * 2 + (use_initflow ? 1 : 0);
   auto it = ctx->graphs.find(key);
@@ -795,10 +825,10 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
     // stored skewed (see VarRefPlanes); returned in natural (h, pitch, per-pixel) order
     const bool is_rec = name[0] == 'r';
     VarRefPlanes bp{};
-    if (!sor_band_plan(L->w, L->h, ctx->sor_single_max, ctx->sor_max_cluster, &bp)) return OFDIS_ERR_UNSUPPORTED;
+    if (!sor_band_plan(L->w, L->h, ctx->sor_rt, ctx->sor_single_max, ctx->sor_max_cluster, ctx->nop, ctx->prm.tv_solverit, &bp)) return OFDIS_ERR_UNSUPPORTED;
     const int nq = is_rec ? (L->nop == 2 ? 8 : 5) : 2;            // float4 (fields) per 4-pixel block
     const int per = is_rec ? (L->nop == 2 ? 8 : 5) : 2;           // floats per pixel
-    const size_t stride = (size_t)bp.nb * bp.ndiag * bp.hpad * nq;  // float4 per frame
+    const size_t stride = (size_t)bp.nb * bp.ndiag * bp.rt * bp.hpad * nq;  // float4 per frame
     if (plane * per > max_floats) return OFDIS_ERR_ARG;
     std::vector<float> raw(stride * 4);
     const float4* base = (is_rec ? ctx->planes.rec : ctx->planes.dudv) + (size_t)fr * stride;

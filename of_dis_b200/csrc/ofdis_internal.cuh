@@ -49,41 +49,62 @@ struct VarRefPlanes {
   float* mask;             // [frames]
   float* avg;              // [frames][C]   0.5*(I1w+I0)            (setup only)
   float* deriv[8];         // Ix Iy Iz Ixx Ixy Iyy Ixz Iyz, each [frames][C]
-  // Band-skewed ("anti-diagonal major") storage shared by assemble_kernel and sor_wave_kernel: the
-  // rows of a level are cut into `nb` bands of `hpad` rows (hpad a power of two; one band per CTA of
-  // the SOR launch).  The 4-pixel block (row j = c*hpad + jl, columns 4I..4I+3) lives at
-  // [band c][d = I + jl][q][jl] with q the float4 inside the block, so that the lanes of a SOR warp
-  // (consecutive rows, same d at a given super-step) touch consecutive 16-byte words and a whole
-  // diagonal of a band is one contiguous bulk copy.  See band_f4() below.
-  float4* dudv;            // [frames][nb][ndiag][2][hpad] float4 = du x4 | dv x4 of a block
-  float4* rec;             // [frames][nb][ndiag][NQ][hpad] float4, NQ = 8 record fields (flow) / 5 (stereo)
+  // Band-skewed ("anti-diagonal major") storage shared by assemble_kernel and sor_wave_kernel.  The
+  // rows of a level are cut into `nb` bands of hpad*rt rows (one band per CTA of the SOR launch); a
+  // band has `hpad` lanes (threads of one sweep; a power of two) of `rt` consecutive rows each
+  // (1, 2 or 4).  The 4-pixel block (row j, columns 4I..4I+3) with band c = j / (hpad*rt), lane
+  // rl = (j mod hpad*rt) / rt and row-in-lane s lives at [band c][d = I + rl][s][q][rl], q the float4
+  // inside the block: the lanes of a SOR warp (same d at a given super-step) touch consecutive
+  // 16-byte words and a whole diagonal of a band is one contiguous bulk copy.  See band_f4() below.
+  float4* dudv;            // [frames][nb][ndiag][rt][2][hpad] float4 = du x4 | dv x4 of a block
+  float4* rec;             // [frames][nb][ndiag][rt][NQ][hpad] float4, NQ = 8 record fields (flow) / 5 (stereo)
   size_t plane;            // pitch*h (natural planes)
   size_t dudv_stride;      // float4 per frame
   size_t rec_stride;       // float4 per frame
-  int hpad, hshift;        // rows per band, log2
+  int hpad;                // lanes per band (threads of one sweep)
+  int rt, rtshift;         // rows per lane, log2
+  int hbshift;             // log2(rows per band = hpad*rt)
   int nb;                  // bands
   int ndiag;               // diagonals stored per band: W4 + hpad + 2
 };
 
+// index of the first float4 (q = 0) of block (I, j) in units of "blocks" -- multiply by NQ, add q,
+// multiply by hpad and add the lane (returned in *lane) for the float4 index
+__host__ __device__ __forceinline__ int band_blk(const VarRefPlanes& pl, int I, int j, int* lane) {
+  const int jl = j & ((pl.hpad << pl.rtshift) - 1), rl = jl >> pl.rtshift;
+  *lane = rl;
+  return (((j >> pl.hbshift) * pl.ndiag + I + rl) << pl.rtshift) + (jl & (pl.rt - 1));
+}
 // float4 index of float4 q of block (I, j) in a band-skewed array with NQ float4 per block
 __host__ __device__ __forceinline__ size_t band_f4(const VarRefPlanes& pl, int I, int j, int q, int NQ) {
-  const int jl = j & (pl.hpad - 1);
-  return (((size_t)(j >> pl.hshift) * pl.ndiag + I + jl) * NQ + q) * pl.hpad + jl;
+  int rl;
+  const int blk = band_blk(pl, I, j, &rl);
+  return ((size_t)blk * NQ + q) * pl.hpad + rl;
 }
 
-// Band plan of a level for the SOR (sor_wave_kernel.cuh): levels of up to `single_max` rows run in
-// one CTA (hpad = rows padded to 32/64/128); taller ones are cut into the smallest bands that still
-// fit a cluster of `max_cluster` CTAs.  Returns false when the level is too tall.
-inline bool sor_band_plan(int w, int h, int single_max, int max_cluster, VarRefPlanes* pl) {
+// Band plan of a level for the SOR (sor_wave_kernel.cuh).  `rt` rows per lane (tiles of 4 columns x
+// rt rows per thread and super-step: the wavefront needs W/4 + h/rt super-steps).  Levels of up to
+// `single_max` lanes run in one CTA (hpad = lanes padded to 32/64/128); taller ones are cut into the
+// smallest bands that still fit a cluster of `max_cluster` CTAs.  Returns false when the level is
+// too tall.
+bool sor_fits(int nop, int hpad, int rt, int K);  // threads and shared memory of one CTA with K sweeps in flight
+inline bool sor_band_plan(int w, int h, int rt, int single_max, int max_cluster, int nop, int K, VarRefPlanes* pl) {
+  const int lanes = (h + rt - 1) / rt;  // lanes the whole level needs
   int hpad = 0;
-  for (int p = 32; p <= 128 && !hpad; p *= 2)
-    if (h <= p && h <= single_max) hpad = p;
-  for (int p = 32; p <= 256 && !hpad; p *= 2)
-    if ((h + p - 1) / p <= max_cluster) hpad = p;
+  // all K sweeps in flight if some band size allows it, else one sweep per launch (K launches per solve)
+  for (int kk = K < 1 ? 1 : K; !hpad; kk = 1) {
+    for (int p = 32; p <= 128 && !hpad; p *= 2)
+      if (lanes <= p && lanes <= single_max && sor_fits(nop, p, rt, kk)) hpad = p;
+    for (int p = 32; p <= 256 && !hpad; p *= 2)
+      if ((lanes + p - 1) / p <= max_cluster && sor_fits(nop, p, rt, kk)) hpad = p;
+    if (kk == 1) break;
+  }
   if (!hpad) return false;
   pl->hpad = hpad;
-  pl->hshift = hpad == 32 ? 5 : (hpad == 64 ? 6 : (hpad == 128 ? 7 : 8));
-  pl->nb = (h + hpad - 1) / hpad;
+  pl->rt = rt;
+  pl->rtshift = rt == 1 ? 0 : (rt == 2 ? 1 : 2);
+  pl->hbshift = (hpad == 32 ? 5 : (hpad == 64 ? 6 : (hpad == 128 ? 7 : 8))) + pl->rtshift;
+  pl->nb = (lanes + hpad - 1) / hpad;
   pl->ndiag = (w + 3) / 4 + hpad + 2;
   return true;
 }

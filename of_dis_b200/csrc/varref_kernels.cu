@@ -153,12 +153,13 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   const int w = g.w, h = g.h, pitch = g.pitch;
   const float* const flow = g.flow + (size_t)frame * g.flow_frame_stride;
   const float* const dudv = reinterpret_cast<const float*>(pl.dudv + (size_t)fr * pl.dudv_stride);
-  const int hpad = pl.hpad, hshift = pl.hshift, ndiag = pl.ndiag;
+  const int hpad = pl.hpad;
   // float index of du of pixel (x,y) in the band-skewed layout (band_f4 with NQ = 2): float4 0 of a
   // block holds du x4, float4 1 (4*hpad floats on) dv x4
-  auto dudv_idx = [hpad, hshift, ndiag](int x, int y) {
-    const int jl = y & (hpad - 1);
-    return ((((y >> hshift) * ndiag + (x >> 2) + jl) * 2) * hpad + jl) * 4 + (x & 3);
+  auto dudv_idx = [&pl, hpad](int x, int y) {
+    int rl;
+    const int blk = band_blk(pl, x >> 2, y, &rl);
+    return ((blk * 2) * hpad + rl) * 4 + (x & 3);
   };
 
   // uu = wx + du (vv likewise); first iteration: uu = wx (refine_variational.cpp:189-190).
@@ -352,8 +353,8 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     const float det = iA11 * iA22 - A12 * A12;
     // record of the 4-pixel block, SoA: float4 f of the block holds field f of its 4 pixels;
     // fields: a11^-1, a12^-1, a22^-1, b1, b2, sh, sv, sv(row above)
-    const int jl = j & (hpad - 1);
-    const int b0 = ((((j >> hshift) * ndiag + (i >> 2) + jl) * 8) * hpad + jl) * 4 + (i & 3);  // band_f4(I, j, 0, 8)
+    int rl;
+    const int b0 = ((band_blk(pl, i >> 2, j, &rl) * 8) * hpad + rl) * 4 + (i & 3);  // band_f4(I, j, 0, 8)
     rec[b0] = iA11 / det;
     rec[b0 + fs] = A12 / -det;
     rec[b0 + 2 * fs] = iA22 / det;
@@ -370,8 +371,8 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     if (j < h - 1) sum += vv;
     if (i < w - 1) sum += hh;
     // stereo record fields: A11 = a11 + sum, b1, sh, sv, sv(row above)
-    const int jl = j & (hpad - 1);
-    const int b0 = ((((j >> hshift) * ndiag + (i >> 2) + jl) * 5) * hpad + jl) * 4 + (i & 3);  // band_f4(I, j, 0, 5)
+    int rl;
+    const int b0 = ((band_blk(pl, i >> 2, j, &rl) * 5) * hpad + rl) * 4 + (i & 3);  // band_f4(I, j, 0, 5)
     rec[b0] = A11 + sum;
     rec[b0 + fs] = B1;
     rec[b0 + 2 * fs] = hh;
@@ -418,17 +419,18 @@ __global__ void __launch_bounds__(256) flow_update_kernel(LevelGeom g, VarRefPla
 
 // Largest number of sweeps one launch can keep in flight: K*hpad compute threads + the producer
 // warp within the kernel's launch bound, stage ring + board within the 227 KB of an SM.
-static int sor_sweeps_per_launch(int nop, int hpad, int K) {
+static int sor_sweeps_per_launch(int nop, int hpad, int rt, int K) {
   int kl = K < 1 ? 1 : K;
-  while (kl > 1 && (kl * hpad + 32 > sor_max_threads(hpad) || sor_smem_bytes(nop, hpad, kl) > 227 * 1024)) --kl;
+  while (kl > 1 && (kl * hpad + 32 > sor_max_threads(hpad) || sor_smem_bytes(nop, hpad, rt, kl) > 227 * 1024)) --kl;
   return kl;
 }
 
-template <int NOP, int HPAD, bool CL>
+template <int NOP, int HPAD, int RT, bool CL>
 static cudaError_t launch_sor_t(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int nf, int kl,
                                 cudaStream_t st) {
-  auto kern = sor_wave_kernel<NOP, HPAD, CL>;
-  const size_t smem = sor_smem_bytes(NOP, HPAD, kl);
+  auto kern = sor_wave_kernel<NOP, HPAD, RT, CL>;
+  const size_t smem = sor_smem_bytes(NOP, HPAD, RT, kl);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   // opt-in shared memory (and cluster size) once per device and instantiation
   static size_t smem_set[64] = {0};
   int dev = 0;
@@ -456,16 +458,25 @@ static cudaError_t launch_sor_t(const LevelGeom& g, const VarRefPlanes& pl, cons
   return cudaLaunchKernelEx(&cfg, kern, g, pl, vp, kl);
 }
 
+template <int NOP, int RT>
+static cudaError_t launch_sor_rt(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int nf, int kl,
+                                 cudaStream_t st) {
+  const bool cl = pl.nb > 1;
+  switch (pl.hpad) {
+    case 32: return cl ? launch_sor_t<NOP, 32, RT, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 32, RT, false>(g, pl, vp, nf, kl, st);
+    case 64: return cl ? launch_sor_t<NOP, 64, RT, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 64, RT, false>(g, pl, vp, nf, kl, st);
+    case 128: return cl ? launch_sor_t<NOP, 128, RT, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 128, RT, false>(g, pl, vp, nf, kl, st);
+    case 256: return cl ? launch_sor_t<NOP, 256, RT, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 256, RT, false>(g, pl, vp, nf, kl, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
 template <int NOP>
 static cudaError_t launch_sor(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int nf, int kl,
                               cudaStream_t st) {
-  const bool cl = pl.nb > 1;
-  switch (pl.hpad) {
-    case 32: return cl ? launch_sor_t<NOP, 32, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 32, false>(g, pl, vp, nf, kl, st);
-    case 64: return cl ? launch_sor_t<NOP, 64, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 64, false>(g, pl, vp, nf, kl, st);
-    case 128: return cl ? launch_sor_t<NOP, 128, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 128, false>(g, pl, vp, nf, kl, st);
-    case 256: return cl ? launch_sor_t<NOP, 256, true>(g, pl, vp, nf, kl, st) : launch_sor_t<NOP, 256, false>(g, pl, vp, nf, kl, st);
-  }
+  if (pl.rt == 1) return launch_sor_rt<NOP, 1>(g, pl, vp, nf, kl, st);
+  if (pl.rt == 2) return launch_sor_rt<NOP, 2>(g, pl, vp, nf, kl, st);
+  if (pl.rt == 4) return launch_sor_rt<NOP, 4>(g, pl, vp, nf, kl, st);
   return cudaErrorInvalidValue;
 }
 
@@ -493,7 +504,7 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
   // many sweeps per launch as the CTA's thread and shared-memory budgets hold (sweeps are sequential,
   // so K sweeps in ceil(K / kl) launches give the same result)
   const int K = vp.n_solver;
-  const int kl = sor_sweeps_per_launch(NOP, pl.hpad, K);
+  const int kl = sor_sweeps_per_launch(NOP, pl.hpad, pl.rt, K);
   for (int it = 0; it < vp.n_inner; ++it) {
     {
       ProfScope scope(prof, KC_VR_ASSEMBLE);
@@ -522,6 +533,10 @@ extern "C" int ofdis_debug_sor_times(long long* dst) {
 }
 #endif
 
+bool sor_fits(int nop, int hpad, int rt, int K) {
+  return K * hpad + 32 <= sor_max_threads(hpad) && sor_smem_bytes(nop, hpad, rt, K) <= 227 * 1024;
+}
+
 int sor_max_cluster_size() {
   // 16 CTAs is a non-portable cluster size: ask the occupancy calculator whether one such cluster
   // of the largest SOR configuration (256-row bands, one sweep) fits this device
@@ -530,8 +545,8 @@ int sor_max_cluster_size() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 8;
   if (cached[dev]) return cached[dev];
   int best = 8;
-  auto kern = sor_wave_kernel<2, 256, true>;
-  const size_t smem = sor_smem_bytes(2, 256, 1);
+  auto kern = sor_wave_kernel<2, 256, 1, true>;
+  const size_t smem = sor_smem_bytes(2, 256, 1, 1);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};

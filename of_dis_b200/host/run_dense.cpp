@@ -65,12 +65,15 @@ bool decode_pnm(const vector<uint8_t>& b, Image8& im, vector<uint8_t>& rgb, int&
       continue;
     }
     int v = 0, d = 0;
-    while (pos < b.size() && isdigit(b[pos])) { v = v * 10 + (b[pos++] - '0'); ++d; }
+    while (pos < b.size() && isdigit(b[pos])) {
+      if (++d > 6) return false;  // no header number has more than 6 digits: no int overflow
+      v = v * 10 + (b[pos++] - '0');
+    }
     if (!d) return false;
     vals[nv++] = v;
   }
   ++pos;  // single whitespace after maxval
-  if (nv < 3 || vals[2] != 255) return false;
+  if (nv < 3 || vals[2] != 255 || vals[0] <= 0 || vals[1] <= 0 || vals[0] > (1 << 15) || vals[1] > (1 << 15)) return false;
   im.w = vals[0];
   im.h = vals[1];
   const size_t n = (size_t)im.w * im.h * ch;
@@ -94,6 +97,7 @@ bool decode_png(const vector<uint8_t>& b, Image8& im, vector<uint8_t>& rgb, int&
     const uint8_t* data = &b[pos + 8];
     if (pos + 12 + len > b.size()) return false;
     if (!memcmp(type, "IHDR", 4)) {
+      if (len < 13) return false;
       im.w = be32(data);
       im.h = be32(data + 4);
       depth = data[8];
@@ -104,7 +108,7 @@ bool decode_png(const vector<uint8_t>& b, Image8& im, vector<uint8_t>& rgb, int&
     else if (!memcmp(type, "IEND", 4)) break;
     pos += 12 + len;
   }
-  if (depth != 8 || interlace != 0 || im.w <= 0 || im.h <= 0) return false;
+  if (depth != 8 || interlace != 0 || im.w <= 0 || im.h <= 0 || im.w > (1 << 15) || im.h > (1 << 15)) return false;
   int spp;  // samples per pixel in the file
   switch (ctype) {
     case 0: spp = 1; break;
@@ -148,6 +152,7 @@ bool decode_png(const vector<uint8_t>& b, Image8& im, vector<uint8_t>& rgb, int&
     const uint8_t* s = &img[i * spp];
     if (ctype == 0 || ctype == 4) rgb[i] = s[0];
     else if (ctype == 3) {
+      if ((size_t)s[0] * 3 + 3 > plte.size()) return false;  // palette index beyond PLTE
       const uint8_t* e = &plte[(size_t)s[0] * 3];
       rgb[i * 3] = e[0]; rgb[i * 3 + 1] = e[1]; rgb[i * 3 + 2] = e[2];
     } else {
@@ -157,12 +162,23 @@ bool decode_png(const vector<uint8_t>& b, Image8& im, vector<uint8_t>& rgb, int&
   return true;
 }
 
-// cv::imread semantics: GRAYSCALE -> 1 channel (BT.601 fixed point of cvtColor), COLOR -> BGR
+// cv::imread semantics: COLOR -> BGR; GRAYSCALE -> 1 channel.  A colour PNM goes through cvtColor's
+// 14-bit BT.601 fixed point, a colour PNG through libpng's png_set_rgb_to_gray(0.299, 0.587): 15-bit
+// coefficients 9797 / 19234 / 3737, truncating (checked against cv2 4.13: both formulas reproduce
+// cv2.imread(..., IMREAD_GRAYSCALE) exactly on random colour images, tests/test_params_io.py).
 bool load_image(const char* path, int want_channels, Image8& im) {
   vector<uint8_t> file, rgb;
   int ch = 0;
   if (!read_file(path, file)) return false;
-  if (!decode_pnm(file, im, rgb, ch) && !decode_png(file, im, rgb, ch)) return false;
+  bool from_png = false;
+  try {
+    if (!decode_pnm(file, im, rgb, ch)) {
+      if (!decode_png(file, im, rgb, ch)) return false;
+      from_png = true;
+    }
+  } catch (const std::exception&) {  // bad_alloc / length errors on malformed headers
+    return false;
+  }
   im.c = want_channels;
   const size_t n = (size_t)im.w * im.h;
   im.px.resize(n * want_channels);
@@ -171,7 +187,8 @@ bool load_image(const char* path, int want_channels, Image8& im) {
       if (ch == 1) im.px[i] = rgb[i];
       else {
         const int r = rgb[i * 3], g = rgb[i * 3 + 1], b = rgb[i * 3 + 2];
-        im.px[i] = (uint8_t)((r * 4899 + g * 9617 + b * 1868 + 8192) >> 14);
+        im.px[i] = from_png ? (uint8_t)((r * 9797 + g * 19234 + b * 3737) >> 15)
+                            : (uint8_t)((r * 4899 + g * 9617 + b * 1868 + 8192) >> 14);
       }
     } else {
       if (ch == 1) im.px[i * 3] = im.px[i * 3 + 1] = im.px[i * 3 + 2] = rgb[i];
@@ -389,7 +406,22 @@ double elapsed_ms(timeval& a) {
 
 }  // namespace
 
-#ifdef OFDIS_BATCH
+#ifdef OFDIS_IMGDUMP
+// Test tool (no GPU): ofdis_imgdump <in.png|pgm|ppm> <gray|color> <out.pnm> -- what load_image() hands to
+// the pipeline, so that tests can compare the decoders with cv2.imread (tests/test_params_io.py).
+int main(int argc, char** argv) {
+  if (argc != 4) return 2;
+  Image8 im;
+  const int want = !strcmp(argv[2], "gray") ? 1 : 3;
+  if (!load_image(argv[1], want, im)) return 1;
+  FILE* f = fopen(argv[3], "wb");
+  if (!f) return 3;
+  fprintf(f, "P%d\n%d %d\n255\n", want == 1 ? 5 : 6, im.w, im.h);
+  fwrite(im.px.data(), 1, im.px.size(), f);  // colour: BGR order, as cv::imread returns it
+  fclose(f);
+  return 0;
+}
+#elif defined(OFDIS_BATCH)
 // Batch front-end: many pairs per launch through the C-ABI's frame dimension.
 //
 //   run_*_*_batch listfile [--batch N] [oppoint | p1 .. p20]

@@ -36,8 +36,8 @@ def test_create_rejects_bad_arguments_without_touching_the_gpu(built_lib):
     cp = prm.to_c()
     # width not divisible by 2^sc_f (oflow.h:87)
     assert built_lib.ofdis_create(ctypes.byref(h), 0, None, ctypes.byref(cp), 2, 1000, 448, 8, 1) == -1
-    # a refinement level taller than 16 bands of 256 rows (the largest SOR cluster): valid in the reference, not built
-    assert built_lib.ofdis_create(ctypes.byref(h), 0, None, ctypes.byref(cp), 2, 1024, 32800, 8, 1) == -3
+    # a refinement level taller than the largest SOR cluster can hold (16 bands of ~256 rows): valid in the reference, not built
+    assert built_lib.ofdis_create(ctypes.byref(h), 0, None, ctypes.byref(cp), 2, 1024, 131104, 8, 1) == -3
     cp.noc = 2
     assert built_lib.ofdis_create(ctypes.byref(h), 0, None, ctypes.byref(cp), 2, 1024, 448, 8, 1) == -1
     assert built_lib.ofdis_destroy(None) == 0

@@ -204,27 +204,36 @@ def test_properties_at_full_size(api):
     assert epe < 0.5, epe
 
 
-def test_tall_level_1024_rows_runs_as_a_cluster_of_eight_bands(api, oracle_port):
+@pytest.mark.parametrize("rt", [1, 2, 4])
+def test_tall_level_1024_rows_runs_as_a_cluster_of_bands(rt, api, oracle_port):
     """Refinement level with exactly 1024 rows (as in BASELINE configs[4]'s level 1; 8 bands of 128 rows,
-    one CTA of a thread-block cluster each): narrow stereo pair so the oracle stays fast."""
+    one CTA of a thread-block cluster each, tiles of 1, 2 or 4 rows per thread): narrow stereo pair so the
+    oracle stays fast."""
     prm = params.from_cli_numbers("2 1 8 8 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split(), noc=1, nop=1)
     i0, i1, _ = synth.synthetic_pair(2048, 96, 1, seed=9, amp=3.0, stereo=True)
     pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
     ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    ctx.set_option("sor_rows_per_thread", rt)
     ctx.upload_pyramids(0, pyr)
     ctx.run(1)
     assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "run h=1024")
     ctx.close()
 
 
-@pytest.mark.parametrize("nop,rows,sweeps", [(2, 1100, 3), (1, 2048, 2)])
-def test_levels_taller_than_1024_rows(nop, rows, sweeps, api, oracle_port):
-    """Levels beyond 8 x 128 rows: bands of 256 rows, one sweep per launch (the round-1 kernel refused these).
-    1100 rows = 5 bands (the last one 76 rows), 2048 rows = the full cluster of 8."""
+@pytest.mark.parametrize("nop,rows,sweeps,rt", [(2, 1100, 3, 2), (1, 2048, 2, 2), (2, 1101, 3, 4), (2, 1100, 3, 1), (1, 4090, 1, 4)])  # 4090 rows need a 16-CTA cluster
+def test_levels_taller_than_1024_rows(nop, rows, sweeps, rt, api, oracle_port):
+    """Levels beyond 8 x 128 rows (the round-1 kernel refused these): more rows per band, fewer sweeps per
+    launch when the stage ring no longer fits; odd heights; 4090 rows = 8 bands of 512 rows, 4 rows per thread."""
     prm = params.from_cli_numbers(("1 0 6 6 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 %d 1.6 0" % sweeps).split(), noc=1, nop=nop)
     i0, i1, _ = synth.synthetic_pair(rows, 72, 1, seed=11, amp=2.0, stereo=(nop == 1))
     pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
-    ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    try:
+        ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    except api.OfdisError:
+        if rows > 2048:
+            pytest.skip("device grants no 16-CTA clusters")
+        raise
+    ctx.set_option("sor_rows_per_thread", rt)
     ctx.upload_pyramids(0, pyr)
     ctx.run(1)
     assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "run h=%d" % rows)
@@ -235,12 +244,13 @@ CLUSTER_CASES = ["cfg2_1024x436_gray_op2", "rgb_op3_l1cost_small", "stereo_op4_s
                  "gray_sor2_rows70", "stereo_sor1_rows100"]
 
 
-@pytest.mark.parametrize("single_max", [32, 64])
+@pytest.mark.parametrize("single_max,rt", [(32, 1), (64, 1), (32, 2)])
 @pytest.mark.parametrize("name", CLUSTER_CASES)
-def test_cluster_sor_on_small_levels_vs_oracle(name, single_max, api, oracle_port):
-    """ofdis_set_option("sor_single_max"): the same levels solved by a cluster of 32- or 64-row bands instead of
-    one CTA (2..5 bands, partial last bands, 1..5 sweeps, flow and stereo) -- dudv after two inner iterations and
-    the whole run, bitwise; two frames per launch so that consecutive clusters share the grid."""
+def test_cluster_sor_on_small_levels_vs_oracle(name, single_max, rt, api, oracle_port):
+    """ofdis_set_option("sor_single_max" / "sor_rows_per_thread"): the same levels solved by a cluster of bands of
+    32 or 64 lanes (1 or 2 rows each) instead of one CTA (2..5 bands, partial last bands, odd heights, 1..5
+    sweeps, flow and stereo) -- dudv after two inner iterations and the whole run, bitwise; two frames per
+    launch so that consecutive clusters share the grid."""
     h, w, ch, mk, amp, stereo = CASES[name]
     prm = mk()
     pyrs = []
@@ -249,6 +259,7 @@ def test_cluster_sor_on_small_levels_vs_oracle(name, single_max, api, oracle_por
         pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
     ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, 2)
     ctx.set_option("sor_single_max", single_max)
+    ctx.set_option("sor_rows_per_thread", rt)
     for f, p in enumerate(pyrs):
         ctx.upload_pyramids(f, p)
     lv = prm.sc_l
@@ -271,8 +282,24 @@ def test_cluster_sor_on_small_levels_vs_oracle(name, single_max, api, oracle_por
     ctx.close()
 
 
+@pytest.mark.parametrize("rt", [1, 4])
+@pytest.mark.parametrize("name", ["cfg2_1024x436_gray_op2", "stereo_op4_small", "gray_p6_nopatnorm_sor5", "gray_sor2_rows70"])
+def test_sor_tile_heights_vs_oracle(name, rt, api, oracle_port):
+    """Tiles of 1 and 4 rows per SOR thread (the default is 2) give the same bits."""
+    h, w, ch, mk, amp, stereo = CASES[name]
+    prm = mk()
+    i0, i1, _ = synth.synthetic_pair(h, w, ch, seed=3, amp=amp, stereo=stereo)
+    pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
+    ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    ctx.set_option("sor_rows_per_thread", rt)
+    ctx.upload_pyramids(0, pyr)
+    ctx.run(1)
+    assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "run rt=%d" % rt)
+    ctx.close()
+
+
 def test_cluster_of_sixteen_bands_where_the_device_grants_it(api, oracle_port):
-    """Non-portable cluster size 16: 1100-row level as 9 bands of 128 rows (all sweeps in flight)."""
+    """Non-portable cluster size 16: 1100-row level as 9 bands of 64 lanes x 2 rows (all sweeps in flight)."""
     prm = params.from_cli_numbers("1 0 6 6 0.05 0.95 0 8 0.4 0 1 0 1 10 10 5 1 3 1.6 0".split(), noc=1, nop=2)
     i0, i1, _ = synth.synthetic_pair(1100, 72, 1, seed=11, amp=2.0)
     pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)

@@ -59,3 +59,69 @@ def test_flo_and_pfm_files(tmp_path):
         assert float(f.readline()) == -1.0
         data = np.fromfile(f, "<f4").reshape(5, 9)
     assert np.array_equal(-data[::-1], disp[..., 0])     # bottom-up rows, negated disparity
+
+
+def _imgdump():
+    import os
+
+    from of_dis_b200 import build
+
+    return os.path.join(build.build_host(), "ofdis_imgdump")
+
+
+@pytest.mark.parametrize("ext", ["png", "ppm"])
+def test_image_loader_equals_cv2_imread(ext, tmp_path):
+    """run_* read images without OpenCV (host/run_dense.cpp load_image): a colour file read as gray must
+    give cv2.imread(IMREAD_GRAYSCALE)'s bytes -- libpng's rgb_to_gray for PNG, cvtColor's fixed point for
+    PPM --, read as colour its BGR bytes; gray files pass through."""
+    import subprocess
+
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    col = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    col[:5] = col[:5, :, :1]  # some r == g == b pixels
+    gray = rng.integers(0, 256, (37, 53), dtype=np.uint8)
+    gext = "pgm" if ext == "ppm" else "png"
+    fc, fg = str(tmp_path / ("c." + ext)), str(tmp_path / ("g." + gext))
+    assert cv2.imwrite(fc, col) and cv2.imwrite(fg, gray)
+    tool = _imgdump()
+    for src, mode, flag in ((fc, "gray", cv2.IMREAD_GRAYSCALE), (fc, "color", cv2.IMREAD_COLOR),
+                            (fg, "gray", cv2.IMREAD_GRAYSCALE), (fg, "color", cv2.IMREAD_COLOR)):
+        out = str(tmp_path / "o.pnm")
+        assert subprocess.run([tool, src, mode, out]).returncode == 0
+        exp = cv2.imread(src, flag)
+        with open(out, "rb") as f:
+            assert f.readline() in (b"P5\n", b"P6\n")
+            w, h = map(int, f.readline().split())
+            f.readline()
+            got = np.frombuffer(f.read(), np.uint8).reshape(exp.shape)
+        assert (w, h) == (53, 37)
+        assert np.array_equal(got, exp), (src, mode, int((got != exp).sum()))
+
+
+def test_image_loader_rejects_malformed_files(tmp_path):
+    """Truncated / hostile headers make load_image fail (exit code 1), never crash."""
+    import struct
+    import subprocess
+    import zlib
+
+    tool = _imgdump()
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+
+    sig = b"\x89PNG\r\n\x1a\n"
+    bad = {
+        "short_ihdr.png": sig + chunk(b"IHDR", b"\0\0\0\x04\0\0\0\x04\x08") + chunk(b"IEND", b""),
+        "huge.png": sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 1 << 30, 1 << 30, 8, 2, 0, 0, 0)) + chunk(b"IEND", b""),
+        "no_plte.png": sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 2, 2, 8, 3, 0, 0, 0)) +
+        chunk(b"IDAT", zlib.compress(b"\0\5\7\0\1\2")) + chunk(b"IEND", b""),
+        "overflow.pgm": b"P5\n99999999999 99999999999\n255\n" + b"\0" * 16,
+        "truncated.pgm": b"P5\n64 64\n255\n" + b"\0" * 100,
+        "empty.png": b"",
+    }
+    for name, data in bad.items():
+        p = tmp_path / name
+        p.write_bytes(data)
+        r = subprocess.run([tool, str(p), "gray", str(tmp_path / "o.pnm")])
+        assert r.returncode == 1, (name, r.returncode)

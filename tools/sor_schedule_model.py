@@ -1,168 +1,175 @@
 """Symbolic model of sor_wave_kernel's data flow (of_dis_b200/csrc/sor_wave_kernel.cuh): every value is
 a tag (I, j, sweep); the model replays the producer's loads, the stage ring, the double-buffered board,
-the cluster halo stores and the in-place (du,dv) writes super-step by super-step and asserts that every
+the cluster halo ring and the in-place (du,dv) writes super-step by super-step and asserts that every
 block reads exactly the operands the lexicographic scan gives it (top/left of this sweep, own/right/
 bottom of the previous one) and that no bulk copy reads a location that is written while the copy may
-still be in flight.  CPU-only; python tools/sor_schedule_model.py [W4 h HPAD K]."""
-import itertools
+still be in flight.  RT = rows per lane (tile of 4 columns x RT rows per thread and super-step).
+CPU-only; python tools/sor_schedule_model.py [W4 h HPAD RT K]."""
 import sys
 
 PF = 3
 
 
-def run(W4, h, HPAD, K, verbose=False):
-    nb = (h + HPAD - 1) // HPAD
+def run(W4, h, HPAD, RT, K, verbose=False):
+    HB = HPAD * RT
+    nb = (h + HB - 1) // HB
     NR = 2 * K + PF
-    hb = HPAD + 2
-    S = W4 + h + 2 * K - 2
-    # global (du,dv): tag of the sweep whose value is stored, per block (I, j); -1 = before this solve
-    glob = {(I, j): -1 for I in range(W4) for j in range(h)}
-    written_at = {}
-    # per CTA state
+    R = (h + RT - 1) // RT
+    S = W4 + R + 2 * K - 2
+    glob = {(I, j): -1 for I in range(W4) for j in range(h)}  # sweep whose value is stored; -1 = before this solve
+
     class CTA:
         pass
+
     ctas = []
     for c in range(nb):
         t = CTA()
-        t.c, t.j0 = c, c * HPAD
-        t.hloc = min(HPAD, h - t.j0)
-        t.S_loc = W4 + t.hloc + 2 * K - 2
-        t.dmax = W4 + t.hloc - 1
-        t.stage = [None] * NR      # each: dict(rec_d, dud_d, halo_I, issued_T, snapshot)
+        t.c, t.j0, t.r0 = c, c * HB, c * HPAD
+        t.hloc = min(HB, h - t.j0)
+        t.nl = (t.hloc + RT - 1) // RT
+        t.S_loc = W4 + t.nl + 2 * K - 2
+        t.dmax = W4 + t.nl - 1
+        t.stage = [None] * NR
         t.ist = 0
-        t.board = [dict(), dict()]  # parity -> {(k, row_index): tag}
-        t.halo = [dict(), dict(), dict()]  # slot -> {(dir, k): tag}; dir 0 from the band above, 1 from below
-        t.thr = {}
-        for k in range(K):
-            for jraw in range(HPAD):
-                if jraw < t.hloc:
-                    t.thr[(k, jraw)] = dict(left=None, own=None, st=0, stp=0)
+        t.board = [dict(), dict()]          # parity -> {(k, board row): tag}
+        t.halo = [dict(), dict(), dict()]   # slot -> {(dir, k): tag}
+        t.thr = {(k, rl): dict(left=[None] * RT, own=[None] * RT, st=0, stp=0, last=None)
+                 for k in range(K) for rl in range(t.nl)}
         ctas.append(t)
-    cur, prev = 0, 1
-    hcur, hprev = 0, 2
+    cur, prev, hcur, hprev = 0, 1, 0, 2
     checked = 0
-    pending = []  # (cta, stage index, wait_T) loads not yet waited for
+    pending = []
     for T in range(-PF, S):
-        stores = []  # (cta index, parity, key, tag) applied at the barrier
-        hstores = []  # halo ring stores (cta index, slot, (dir, k), tag)
-        gwrites = []
+        stores, hstores, gwrites = [], [], []
         for t in ctas:
-            tl = T - t.j0
-            # ---- producer
+            tl = T - t.r0
             n = tl + PF
-            if 0 <= n < t.S_loc:
-                d = min(n, t.dmax)
+            if 0 <= n < t.S_loc:  # producer
                 d1 = min(n + 1, t.dmax)
                 ih = min(max(n - (HPAD - 1), 0), W4 - 1)
                 snap = {}
-                for jl in range(HPAD):           # (du,dv) diagonal d1 of this band
-                    I = d1 - jl
-                    if 0 <= I < W4 and jl < t.hloc:
-                        snap[("dud", jl)] = ((I, t.j0 + jl), glob[(I, t.j0 + jl)])
+                for rl in range(t.nl):
+                    I = d1 - rl
+                    for s in range(RT):
+                        j = t.j0 + rl * RT + s
+                        if 0 <= I < W4 and j < h:
+                            snap[("dud", rl, s)] = ((I, j), glob[(I, j)])
                 if t.c + 1 < nb:
-                    snap["halo"] = ((ih, t.j0 + HPAD), glob[(ih, t.j0 + HPAD)])
-                t.stage[t.ist] = dict(n=n, rec_d=d, dud_d=d1, halo_I=ih, snap=snap, issued=T)
-                pending.append((t, t.ist, t.j0 + n - 1))  # waited for before the barrier ending local step n-1
+                    snap["halo"] = ((ih, t.j0 + HB), glob[(ih, t.j0 + HB)])
+                t.stage[t.ist] = dict(n=n, rec_d=min(n, t.dmax), dud_d=d1, halo_I=ih, snap=snap, issued=T)
+                pending.append((t, t.ist, t.r0 + n - 1))
                 t.ist = (t.ist + 1) % NR
-            # ---- compute threads
-            for (k, jl), th in t.thr.items():
+            for (k, rl), th in t.thr.items():
                 n = tl - 2 * k
-                I = n - jl
-                j = t.j0 + jl
-                warp_lo = jl & ~31
-                warp_hi = min(warp_lo + 31, t.hloc - 1)
-                active = tl >= 0 and warp_lo <= n + 1 and warp_hi > n - W4
+                I = n - rl
+                wlo = rl & ~31
+                whi = min(wlo + 31, t.nl - 1)
+                active = tl >= 0 and wlo <= n + 1 and whi > n - W4
+                in_range = 0 <= I < W4
                 if active:
                     st = t.stage[th["st"]]
-                    in_range = 0 <= I < W4
-                    if in_range:  # records of the block: stage of load n, still resident for every sweep
-                        assert st is not None and st["n"] == n, ("stage of load n", T, t.c, k, jl, st and st["n"], n)
-                        assert st["rec_d"] == min(n, t.dmax) == I + jl
-                        assert st["issued"] < T, "load must have been issued (and waited for) before use"
+                    if in_range:
+                        assert st is not None and st["n"] == n and st["rec_d"] == I + rl and st["issued"] < T
+                    own = list(th["own"])
+                    rf = [None] * RT
+                    nxt = [None] * RT
                     if k == 0:
                         if in_range:
-                            # own: diagonal n staged with load n-1 (or global for n == 0)
-                            if n >= 1:
-                                sp = t.stage[th["stp"]]
-                                assert sp["n"] == n - 1 and sp["dud_d"] == n, ("own stage", T, t.c, jl)
-                                own = sp["snap"][("dud", jl)]
-                            else:
-                                own = ((I, j), glob[(I, j)])
-                            assert own == ((I, j), -1), ("own", own, I, j)
-                            if I + 1 < W4:
-                                assert st["dud_d"] == n + 1
-                                rf = st["snap"][("dud", jl)]
-                                assert rf == ((I + 1, j), -1), ("rf", rf)
-                            if j + 1 < h:
-                                if jl + 1 < HPAD:
-                                    bot = st["snap"][("dud", jl + 1)]
+                            for s in range(RT):
+                                j = t.j0 + rl * RT + s
+                                if j >= h:
+                                    continue
+                                if n >= 1:
+                                    sp = t.stage[th["stp"]]
+                                    assert sp["n"] == n - 1 and sp["dud_d"] == n
+                                    own[s] = sp["snap"][("dud", rl, s)]
                                 else:
-                                    assert st["halo_I"] == I, ("halo block", st["halo_I"], I)
+                                    own[s] = ((I, j), glob[(I, j)])
+                                assert own[s] == ((I, j), -1), ("own", own[s])
+                                if I + 1 < W4:
+                                    assert st["dud_d"] == n + 1
+                                    assert st["snap"][("dud", rl, s)] == ((I + 1, j), -1)
+                            jb = t.j0 + rl * RT + RT  # row below the tile
+                            if jb < h:
+                                if rl + 1 < HPAD:
+                                    bot = st["snap"][("dud", rl + 1, 0)]
+                                else:
+                                    assert st["halo_I"] == I
                                     bot = st["snap"]["halo"]
-                                assert bot == ((I, j + 1), -1), ("bot k0", bot, I, j)
+                                assert bot == ((I, jb), -1), ("bot k0", bot, I, jb)
                     else:
-                        nxt = t.board[prev].get((k - 1, jl + 1))
+                        for s in range(RT):
+                            nxt[s] = t.board[prev].get((k - 1, rl * RT + s + 1))
+                        if t.c + 1 < nb and rl == t.nl - 1:
+                            botX = t.halo[hprev].get((1, k - 1))
+                        else:
+                            botX = t.board[prev].get((k - 1, rl * RT + RT + 1))
                         if in_range:
-                            assert th["own"] == (I, j, k - 1), ("own k>0", th["own"], (I, j, k - 1), T)
-                            if I + 1 < W4:
-                                assert nxt == (I + 1, j, k - 1), ("right", nxt, (I + 1, j, k - 1), T)
-                            if j + 1 < h:
-                                if nb > 1 and t.c + 1 < nb and jl == t.hloc - 1:
-                                    bot = t.halo[hprev].get((1, k - 1))
-                                else:
-                                    bot = t.board[prev].get((k - 1, jl + 2))
-                                assert bot == (I, j + 1, k - 1), ("bot", bot, (I, j + 1, k - 1), T, t.c, k, jl)
+                            for s in range(RT):
+                                j = t.j0 + rl * RT + s
+                                if j >= h:
+                                    continue
+                                assert own[s] == (I, j, k - 1), ("own k>0", own[s], (I, j, k - 1), T)
+                                if I + 1 < W4:
+                                    assert nxt[s] == (I + 1, j, k - 1), ("right", nxt[s], (I + 1, j, k - 1))
+                                if j + 1 < h:
+                                    b = own[s + 1] if s + 1 < RT else botX
+                                    assert b == (I, j + 1, k - 1), ("bot", b, (I, j + 1, k - 1), T, t.c, k, rl, s)
+                    topX = t.halo[hprev].get((0, k)) if (t.c > 0 and rl == 0) else t.board[prev].get((k, rl * RT))
+                    new = [None] * RT
+                    for s in range(RT):
+                        j = t.j0 + rl * RT + s
+                        if in_range and j < h:
+                            if j > 0:
+                                top = topX if s == 0 else new[s - 1]
+                                assert top == (I, j - 1, k), ("top", top, (I, j - 1, k), T, t.c, k, rl, s)
+                            if I > 0:
+                                assert th["left"][s] == (I - 1, j, k), ("left", th["left"][s], (I - 1, j, k))
+                            checked += 1
+                            new[s] = (I, j, k)
+                            if k == K - 1:
+                                gwrites.append(((I, j), k))
+                        else:
+                            new[s] = ("junk", T, t.c, k, rl, s)
+                        th["left"][s] = new[s]
+                        stores.append((t.c, cur, (k, rl * RT + s + 1), new[s]))
+                    th["last"] = new
+                    if k > 0:
                         th["own"] = nxt
-                    if in_range:
-                        if j > 0:
-                            top = t.halo[hprev].get((0, k)) if (nb > 1 and t.c > 0 and jl == 0) else t.board[prev].get((k, jl))
-                            assert top == (I, j - 1, k), ("top", top, (I, j - 1, k), T, t.c, k, jl)
-                        if I > 0:
-                            assert th["left"] == (I - 1, j, k), ("left", th["left"], (I - 1, j, k))
-                        checked += 1
-                    tag = (I, j, k) if in_range else ("junk", T, t.c, k, jl)
-                    th["left"] = tag
-                    stores.append((t.c, cur, (k, jl + 1), tag))
-                    th["last"] = tag
-                # unconditional send of the latest block to the neighbouring band's halo ring
-                if nb > 1 and "last" in th:
-                    if jl == 0 and t.c > 0:
-                        hstores.append((t.c - 1, hcur, (1, k), th["last"]))
-                    elif jl == t.hloc - 1 and t.c + 1 < nb:
-                        hstores.append((t.c + 1, hcur, (0, k), th["last"]))
-                if active:
-                    if k == K - 1 and in_range:
-                        gwrites.append(((I, j), k))
+                if nb > 1 and th["last"] is not None:  # unconditional send of the latest tile row
+                    if rl == 0 and t.c > 0:
+                        hstores.append((t.c - 1, hcur, (1, k), th["last"][0]))
+                    elif rl == t.nl - 1 and t.c + 1 < nb:
+                        hstores.append((t.c + 1, hcur, (0, k), th["last"][RT - 1]))
                 if n >= 0:
                     th["stp"] = th["st"]
                     th["st"] = (th["st"] + 1) % NR
-        # barrier: stores become visible, global writes land
         for ci, par, key, tag in stores:
             ctas[ci].board[par][key] = tag
         for ci, slot, key, tag in hstores:
             ctas[ci].halo[slot][key] = tag
         for key, k in gwrites:
-            # no bulk copy that may still be in flight may have this block as its source
             for t, si, wait_T in pending:
-                stg = t.stage[si]
                 if wait_T >= T:
-                    for what, (blk, _) in stg["snap"].items():
-                        assert blk != key, ("in-place write races a bulk copy", key, T, t.c, stg["n"])
+                    for what, (blkk, _) in t.stage[si]["snap"].items():
+                        assert blkk != key, ("in-place write races a bulk copy", key, T, t.c)
             assert glob[key] == -1
             glob[key] = k
-        pending = [(t, si, w) for (t, si, w) in pending if w >= T]
+        pending = [(t, si, wt) for (t, si, wt) in pending if wt >= T]
         cur, prev = prev, cur
         hprev, hcur = hcur, (hcur + 1) % 3
     assert checked == W4 * h * K, (checked, W4 * h * K)
     assert all(v == K - 1 for v in glob.values())
     if verbose:
-        print("ok: W4=%d h=%d HPAD=%d K=%d bands=%d, %d block updates checked" % (W4, h, HPAD, K, nb, checked))
+        print("ok: W4=%d h=%d HPAD=%d RT=%d K=%d bands=%d steps=%d, %d block updates checked" % (W4, h, HPAD, RT, K, nb, S, checked))
 
 
 if __name__ == "__main__":
-    if len(sys.argv) == 5:
+    if len(sys.argv) == 6:
         run(*map(int, sys.argv[1:]), verbose=True)
     else:
-        for W4, h, HPAD, K in [(5, 20, 32, 3), (9, 70, 32, 2), (3, 64, 32, 1), (12, 100, 32, 3), (7, 33, 32, 5),
-                               (20, 130, 64, 3), (4, 200, 64, 1), (16, 56, 64, 3), (2, 96, 32, 2), (1, 65, 32, 3)]:
-            run(W4, h, HPAD, K, verbose=True)
+        for W4, h, HPAD, RT, K in [(5, 20, 32, 1, 3), (9, 70, 32, 1, 2), (12, 100, 32, 1, 3), (7, 33, 32, 1, 5),
+                                   (5, 20, 32, 2, 3), (9, 70, 32, 2, 2), (12, 133, 32, 2, 3), (7, 65, 32, 2, 5),
+                                   (3, 64, 32, 2, 1), (16, 56, 32, 2, 3), (6, 257, 32, 4, 3), (4, 130, 32, 4, 2),
+                                   (20, 300, 64, 2, 3), (2, 96, 32, 4, 1), (1, 65, 32, 2, 3), (8, 17, 32, 4, 3)]:
+            run(W4, h, HPAD, RT, K, verbose=True)
