@@ -14,6 +14,11 @@
 // [slot][thread] columns (conflict free, private to the thread), staged once.
 // The bilinear taps of I1 are plain LDGs: the (P+1)x(P+1) window of a patch
 // moves by a fraction of a pixel per iteration and stays L1-resident.
+#include <cstdint>
+#include <cstring>
+
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "ofdis_internal.cuh"
 
 namespace ofdis {
@@ -521,19 +526,35 @@ __global__ void __launch_bounds__(256) patch_p8c1_kernel(LevelGeom g, PatchParam
 //     shared memory the same taps are 4 LDS with at most a 2-way bank conflict between patches;
 //   * element offsets are walked incrementally (no offset table).
 // Arithmetic (operand order, reduction tree, stop tests) is that of patch_optimize_kernel.
+//
+// TMA = true is the north-star's variant of the window fill: one lane of the patch issues a tensor
+// tile copy (cp.async.bulk.tensor.3d -> UTMALDG; box = window, coordinates (x*C, y, frame) in a
+// tensor map over the padded I1 frames, out-of-image cells zero-filled by the TMA unit) and the
+// patch's 8 lanes wait on an mbarrier, instead of 8 lanes x ~37 LDG+STS.  It needs the row pitch of
+// the padded image to be a multiple of 16 bytes (tensor-map rule), a box whose inner extent is a
+// multiple of 16 bytes (window rows padded from 17 to 20 floats, RGB 51 to 52) and 128-byte aligned
+// windows; A/B in DESIGN.md section 5 (ofdis_set_option "patch_window_tma").
 template <int C> struct PwCfg {
   static constexpr int P = 12, M = 2, W = P + 1 + 2 * M, WC = W * C, PC = P * C, N = P * P * C, NK = N / 8;
+  static constexpr int WCB = (WC + 3) / 4 * 4;  // TMA: window row pitch (floats), inner box extent
+};
+template <int NOP, int C, bool TMA> struct PwWin {
+  static constexpr int WH = (NOP == 2) ? PwCfg<C>::W : PwCfg<C>::P + 1;          // window rows
+  static constexpr int PITCH = TMA ? PwCfg<C>::WCB : PwCfg<C>::WC;               // floats per window row
+  static constexpr int WIN = TMA ? (WH * PITCH * 4 + 127) / 128 * 32 : WH * PITCH;  // floats per window (TMA: 128-byte aligned)
 };
 
-template <int NOP, int C>
+template <int NOP, int C, bool TMA>
 __global__ void __launch_bounds__(256, C == 1 ? 2 : 1) patch_p12_kernel(LevelGeom g, PatchParams pp, int f0,
-                                                                        int init_from_coarser) {
+                                                                        int init_from_coarser,
+                                                                        const __grid_constant__ CUtensorMap tmap) {
   using Cfg = PwCfg<C>;
-  constexpr int P = Cfg::P, M = Cfg::M, W = Cfg::W, WC = Cfg::WC, PC = Cfg::PC, NK = Cfg::NK;
-  constexpr int WH = (NOP == 2) ? W : P + 1;  // window rows
-  constexpr int WIN = WH * WC;                // floats per window
+  constexpr int P = Cfg::P, M = Cfg::M, W = Cfg::W, PC = Cfg::PC, NK = Cfg::NK;
+  constexpr int WH = PwWin<NOP, C, TMA>::WH;    // window rows
+  constexpr int WC = PwWin<NOP, C, TMA>::PITCH;  // floats per window row
+  constexpr int WIN = PwWin<NOP, C, TMA>::WIN;  // floats per window
   constexpr bool G_REG = (C == 1);            // template gradients in registers
-  extern __shared__ float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int l8 = tid & 7;
   const int frame = f0 + blockIdx.y;
@@ -543,6 +564,16 @@ __global__ void __launch_bounds__(256, C == 1 ? 2 : 1) patch_p12_kernel(LevelGeo
   float* const win = smem + (tid >> 3) * WIN;                  // this patch's window
   float* const sGx = smem + (nthr >> 3) * WIN + tid;           // RGB: gradient columns [k][thread]
   float* const sGy = sGx + NK * nthr;
+  // TMA: one mbarrier per patch behind the windows (and the gradient columns)
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem + (nthr >> 3) * WIN + (G_REG ? 0 : 2 * NK * nthr)) + 8u * (tid >> 3);
+  unsigned wphase = 0;
+  if (TMA) {
+    if (l8 == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(1u) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
   const int rowC = g.tmp_w * C;
 
   const float* i0 = g.img[0] + (size_t)frame * g.img_fs[0];
@@ -673,7 +704,29 @@ __global__ void __launch_bounds__(256, C == 1 ? 2 : 1) patch_p12_kernel(LevelGeo
           uy = (NOP == 2) ? M : 0;
         }
       }
-      if (__any_sync(FULL, restage)) {
+      if (TMA) {
+        if (__any_sync(FULL, restage)) {
+          __syncwarp();  // every lane has finished reading the previous window
+          if (restage) {
+            if (l8 == 0) {
+              const unsigned dst = (unsigned)__cvta_generic_to_shared(win);
+              // the lanes' generic-proxy reads of the old window come before the async-proxy write
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)(WH * WC * 4)) : "memory");
+              asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                           ::"r"(dst), "l"(&tmap), "r"(mbar), "r"(wx0 * C), "r"(wy0), "r"(frame)
+                           : "memory");
+            }
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tPW_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra PD_%=;\n\tbra PW_%=;\n\tPD_%=:\n\t}" ::"r"(mbar), "r"(wphase)
+                : "memory");
+            wphase ^= 1u;
+          }
+          __syncwarp();
+        }
+      } else if (__any_sync(FULL, restage)) {
         __syncwarp();  // every lane has finished reading the previous window
         if (restage) {
           const int xlo = wx0 * C, xmax = g.tmp_w * C - 1;
@@ -986,18 +1039,50 @@ int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int
     const int threads12 = 256;
     const dim3 grid12((g.np + threads12 / 8 - 1) / (threads12 / 8), f1 - f0);
     const int init = init_from_coarser ? 1 : 0;
-#define OFDIS_P12(NOPv, Cv)                                                                                        \
+    // TMA window fill (option "patch_window_tma"): needs a tensor map over the padded I1 frames, i.e.
+    // row pitch and frame stride multiples of 16 bytes; other levels keep the LDG fill
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    bool tma = false;
+    if (pp.window_tma && ((size_t)g.tmp_w * g.noc * 4) % 16 == 0 && (g.img_fs[3] * 4) % 16 == 0 &&
+        ((uintptr_t)g.img[3]) % 16 == 0) {
+      typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      static EncodeFn encode = nullptr;
+      if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+          encode = (EncodeFn)fn;
+      }
+      if (encode) {
+        const int WH = (g.nop == 2) ? PwCfg<1>::W : PwCfg<1>::P + 1;
+        const int WCB = (g.noc == 1) ? PwCfg<1>::WCB : PwCfg<3>::WCB;
+        const cuuint64_t dims[3] = {(cuuint64_t)g.tmp_w * g.noc, (cuuint64_t)g.tmp_h, (cuuint64_t)f1};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.tmp_w * g.noc * 4, (cuuint64_t)g.img_fs[3] * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)WCB, (cuuint32_t)WH, 1u}, estr[3] = {1u, 1u, 1u};
+        tma = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.img[3]), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      }
+    }
+#define OFDIS_P12(NOPv, Cv, TMAv)                                                                                   \
   do {                                                                                                             \
-    constexpr int WH = (NOPv == 2) ? PwCfg<Cv>::W : PwCfg<Cv>::P + 1;                                              \
-    const size_t sm = sizeof(float) * ((size_t)(threads12 / 8) * WH * PwCfg<Cv>::WC +                              \
-                                       (Cv == 1 ? 0 : (size_t)2 * PwCfg<Cv>::NK * threads12));                     \
-    if (sm > 48 * 1024) cudaFuncSetAttribute(patch_p12_kernel<NOPv, Cv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-    patch_p12_kernel<NOPv, Cv><<<grid12, threads12, sm, st>>>(g, pp, f0, init);                                    \
+    const size_t sm = sizeof(float) * ((size_t)(threads12 / 8) * PwWin<NOPv, Cv, TMAv>::WIN +                       \
+                                       (Cv == 1 ? 0 : (size_t)2 * PwCfg<Cv>::NK * threads12)) +                    \
+                      (TMAv ? 8 * (threads12 / 8) : 0);                                                            \
+    if (sm > 48 * 1024)                                                                                            \
+      cudaFuncSetAttribute(patch_p12_kernel<NOPv, Cv, TMAv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+    patch_p12_kernel<NOPv, Cv, TMAv><<<grid12, threads12, sm, st>>>(g, pp, f0, init, tmap);                         \
   } while (0)
-    if (g.nop == 2 && g.noc == 1) OFDIS_P12(2, 1);
-    else if (g.nop == 2) OFDIS_P12(2, 3);
-    else if (g.noc == 1) OFDIS_P12(1, 1);
-    else OFDIS_P12(1, 3);
+#define OFDIS_P12T(NOPv, Cv) do { if (tma) OFDIS_P12(NOPv, Cv, true); else OFDIS_P12(NOPv, Cv, false); } while (0)
+    if (g.nop == 2 && g.noc == 1) OFDIS_P12T(2, 1);
+    else if (g.nop == 2) OFDIS_P12T(2, 3);
+    else if (g.noc == 1) OFDIS_P12T(1, 1);
+    else OFDIS_P12T(1, 3);
+#undef OFDIS_P12T
 #undef OFDIS_P12
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }

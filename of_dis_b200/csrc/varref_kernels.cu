@@ -545,13 +545,13 @@ int sor_max_cluster_size() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 8;
   if (cached[dev]) return cached[dev];
   int best = 8;
-  auto kern = sor_wave_kernel<2, 256, 1, true>;
-  const size_t smem = sor_smem_bytes(2, 256, 1, 1);
+  auto kern = sor_wave_kernel<2, 128, 1, true>;
+  const size_t smem = sor_smem_bytes(2, 128, 1, 3);  // 128-row bands, 3 sweeps in flight: the largest common configuration
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(16);
-    cfg.blockDim = dim3(288);
+    cfg.blockDim = dim3(3 * 128 + 32);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

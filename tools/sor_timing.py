@@ -17,9 +17,11 @@ ctx.sync()
 buf = np.zeros(64 * 8 * 16, np.int64)
 assert api.lib().ofdis_debug_sor_times(buf.ctypes.data_as(ctypes.c_void_p)) == 0
 t = buf.reshape(64, 8, 16)[:7, :, :7]   # last launch = level 3 (6 compute warps + the producer), steps 40..47
-names = ["start", "mbarwait", "lds", "prep", "chain", "stores", "barrier"]
+# compute warps stamp slots 0 (step start), 2 (operands loaded), 4 (arithmetic done), 5 (stores issued), 6 (barrier passed);
+# the producer 0 (start), 1 (bulk copies issued), 2 (stage mbarrier passed), 5 (halo mbarriers passed), 6 (barrier passed)
 for wp in range(7):
-    d = np.diff(t[wp], axis=1)          # per-step phase durations
-    role = "producer (issue, -, stage wait, -, -, halo wait, barrier)" if wp == 6 else "k=%d rows %d.." % (wp // 2, 32 * (wp % 2))
-    print("warp %d %s: mean cycles per phase %s | step total %.0f" %
-          (wp, role, dict(zip(names[1:], d.mean(0).round(0))), (t[wp, 1:, 0] - t[wp, :-1, 0]).mean()))
+    slots = [0, 1, 2, 5, 6] if wp == 6 else [0, 2, 4, 5, 6]
+    names = ["issue", "stage wait", "halo wait", "barrier"] if wp == 6 else ["loads", "arithmetic", "stores+prefetch", "barrier"]
+    d = np.diff(t[wp][:, slots], axis=1).mean(0).round(0)
+    role = "producer" if wp == 6 else "k=%d rows %d.." % (wp // 2, 32 * (wp % 2))
+    print("warp %d %-14s %s | step %.0f cycles" % (wp, role, dict(zip(names, d)), (t[wp, 1:, 0] - t[wp, :-1, 0]).mean()))
