@@ -296,29 +296,29 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
     }
   }
   if (ok && prm->usetvref) {
-    // refinement planes sized for the finest level: mask, avg[C], 8 x deriv[C], dudv (2), rec (8)
+    // refinement planes sized for the finest level: mask, avg[C], 8 x deriv[C], and the SOR's lane rows
     const LevelGeom& Lf = ctx->lev[0];
     const size_t plane = (size_t)Lf.pitch * Lf.h;
     const int C = prm->noc;
-    // band-skewed SOR arrays: nb bands x (W4 + hpad + 2) diagonals x rt rows x hpad lanes, 8 (rec) + 2
-    // (dudv) float4 per block; sized for the largest level under every plan ofdis_set_option can select
-    size_t diag = 0;
+    // band-skewed SOR array: nb bands x (W4 + hpad + 2) diagonals x hpad lanes x lpitch float4; sized for
+    // the largest level under every plan ofdis_set_option can select
+    size_t recf4 = 0;
     for (const LevelGeom& L : ctx->lev)
       for (int mc = 8; mc <= ctx->sor_dev_cluster; mc += 8)
         for (int sm = 32; sm <= 128; sm *= 2)
           for (int rt = 1; rt <= 4; rt *= 2) {
             VarRefPlanes t{};
-            if (sor_band_plan(L.w, L.h, rt, sm, mc, nop, prm->tv_solverit, &t)) diag = std::max(diag, (size_t)t.nb * t.ndiag * t.rt * t.hpad);
+            if (sor_band_plan(L.w, L.h, rt, sm, mc, nop, prm->tv_solverit, &t))
+              recf4 = std::max(recf4, (size_t)t.nb * t.ndiag * t.hpad * t.lpitch);
           }
-    const size_t per_frame = plane * (1 + C + 8 * C) + diag * 4 * (8 + 2);
+    const size_t per_frame = plane * (1 + C + 8 * C) + recf4 * 4;
     ok = dalloc((void**)&ctx->d_planes, sizeof(float) * per_frame * cap);
     if (ok) {
-      // never-written record slots (wavefront ramps, padded rows) are read by idle SOR lanes: keep them finite
+      // never-written lane rows (wavefront ramps, padded lanes) are read by idle SOR lanes: keep them finite
       cudaMemsetAsync(ctx->d_planes, 0, sizeof(float) * per_frame * cap, ctx->stream);
       float* q = ctx->d_planes;
       VarRefPlanes& P = ctx->planes;
-      P.rec = reinterpret_cast<float4*>(q); q += diag * 4 * 8 * cap;   // records first (alignment)
-      P.dudv = reinterpret_cast<float4*>(q); q += diag * 4 * 2 * cap;
+      P.rec = reinterpret_cast<float4*>(q); q += recf4 * 4 * cap;   // first (alignment)
       P.mask = q; q += plane * cap;
       P.avg = q; q += plane * C * cap;
       for (int k = 0; k < 8; ++k) { P.deriv[k] = q; q += plane * C * cap; }
@@ -657,11 +657,7 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   pl.plane = (size_t)L->pitch * L->h;
   if (!sor_band_plan(L->w, L->h, ctx->sor_rt, ctx->sor_single_max, ctx->sor_max_cluster, ctx->nop, ctx->prm.tv_solverit, &pl))
     return fail(ctx, OFDIS_ERR_UNSUPPORTED, "varref_refine: level too tall for the largest SOR cluster");
-  {
-    const size_t diag = (size_t)pl.nb * pl.ndiag * pl.rt * pl.hpad;
-    pl.rec_stride = diag * (L->nop == 2 ? 8 : 5);
-    pl.dudv_stride = diag * 2;
-  }
+  pl.rec_stride = (size_t)pl.nb * pl.ndiag * pl.hpad * pl.lpitch;
   // usefbcon: both directions are refined except on the last level (oflow.cpp:285-294)
   const int D = ctx->dirs;
   const bool fwd_only = (D == 2 && level == ctx->prm.sc_l);
@@ -830,19 +826,18 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
     const bool is_rec = name[0] == 'r';
     VarRefPlanes bp{};
     if (!sor_band_plan(L->w, L->h, ctx->sor_rt, ctx->sor_single_max, ctx->sor_max_cluster, ctx->nop, ctx->prm.tv_solverit, &bp)) return OFDIS_ERR_UNSUPPORTED;
-    const int nq = is_rec ? (L->nop == 2 ? 8 : 5) : 2;            // float4 (fields) per 4-pixel block
-    const int per = is_rec ? (L->nop == 2 ? 8 : 5) : 2;           // floats per pixel
-    const size_t stride = (size_t)bp.nb * bp.ndiag * bp.rt * bp.hpad * nq;  // float4 per frame
+    const int per = is_rec ? bp.nq : 2;                              // floats per pixel
+    const size_t stride = (size_t)bp.nb * bp.ndiag * bp.hpad * bp.lpitch;  // float4 per frame
     if (plane * per > max_floats) return OFDIS_ERR_ARG;
     std::vector<float> raw(stride * 4);
-    const float4* base = (is_rec ? ctx->planes.rec : ctx->planes.dudv) + (size_t)fr * stride;
+    const float4* base = ctx->planes.rec + (size_t)fr * stride;
     if (cudaMemcpyAsync(raw.data(), base, sizeof(float) * raw.size(), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return OFDIS_ERR_CUDA;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return OFDIS_ERR_CUDA;
     for (int j = 0; j < L->h; ++j)
       for (int i = 0; i < L->w; ++i)
         for (int e = 0; e < per; ++e) {
-          // both are SoA inside the block: float4 e holds field e of the block's 4 pixels
-          const size_t f4 = band_f4(bp, i >> 2, j, e, nq);
+          // chunk e of the block's lane row holds field e of its 4 pixels; (du,dv) are chunks nq, nq+1
+          const size_t f4 = band_f4(bp, i >> 2, j, is_rec ? e : bp.nq + e);
           dst[((size_t)j * L->pitch + i) * per + e] = raw[f4 * 4 + (i & 3)];
         }
     return (long)(plane * per);

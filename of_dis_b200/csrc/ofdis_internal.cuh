@@ -53,34 +53,33 @@ struct VarRefPlanes {
   // Band-skewed ("anti-diagonal major") storage shared by assemble_kernel and sor_wave_kernel.  The
   // rows of a level are cut into `nb` bands of hpad*rt rows (one band per CTA of the SOR launch); a
   // band has `hpad` lanes (threads of one sweep; a power of two) of `rt` consecutive rows each
-  // (1, 2 or 4).  The 4-pixel block (row j, columns 4I..4I+3) with band c = j / (hpad*rt), lane
-  // rl = (j mod hpad*rt) / rt and row-in-lane s lives at [band c][d = I + rl][s][q][rl], q the float4
-  // inside the block: the lanes of a SOR warp (same d at a given super-step) touch consecutive
-  // 16-byte words and a whole diagonal of a band is one contiguous bulk copy.  See band_f4() below.
-  float4* dudv;            // [frames][nb][ndiag][rt][2][hpad] float4 = du x4 | dv x4 of a block
-  float4* rec;             // [frames][nb][ndiag][rt][NQ][hpad] float4, NQ = 8 record fields (flow) / 5 (stereo)
+  // (1, 2 or 4).  Everything one lane needs for the 4-pixel blocks (rows rl*rt .. rl*rt+rt-1 of the
+  // band, columns 4I..4I+3) of one super-step is ONE contiguous "lane row":
+  //     [band c][d = I + rl][lane rl][ rt x (NQ record fields | du x4 | dv x4) float4, pad to odd ]
+  // so that (a) the lanes that hold a block on diagonal d -- max(0, d-W4+1) .. min(d, lanes-1) --
+  // are one contiguous piece of memory: the SOR's producer fetches exactly the occupied part of a
+  // diagonal with one bulk copy (no bytes for the empty corners of the skew), and (b) with an odd
+  // number of 16-byte words per lane row the lanes of a warp read any one field without a
+  // shared-memory bank conflict.  (du,dv) live in the same lane row as the records (the last sweep
+  // writes them in place).
+  float4* rec;             // [frames][nb][ndiag][hpad][lpitch] float4
   size_t plane;            // pitch*h (natural planes)
-  size_t dudv_stride;      // float4 per frame
   size_t rec_stride;       // float4 per frame
   int hpad;                // lanes per band (threads of one sweep)
   int rt, rtshift;         // rows per lane, log2
   int hbshift;             // log2(rows per band = hpad*rt)
   int nb;                  // bands
   int ndiag;               // diagonals stored per band: W4 + hpad + 2
+  int nq;                  // record fields per block: 8 (flow) / 5 (stereo); chunk nq = du, nq+1 = dv
+  int lpitch;              // float4 per lane row: rt*(nq+2), made odd
 };
 
-// index of the first float4 (q = 0) of block (I, j) in units of "blocks" -- multiply by NQ, add q,
-// multiply by hpad and add the lane (returned in *lane) for the float4 index
-__host__ __device__ __forceinline__ int band_blk(const VarRefPlanes& pl, int I, int j, int* lane) {
-  const int jl = j & ((pl.hpad << pl.rtshift) - 1), rl = jl >> pl.rtshift;
-  *lane = rl;
-  return (((j >> pl.hbshift) * pl.ndiag + I + rl) << pl.rtshift) + (jl & (pl.rt - 1));
-}
-// float4 index of float4 q of block (I, j) in a band-skewed array with NQ float4 per block
-__host__ __device__ __forceinline__ size_t band_f4(const VarRefPlanes& pl, int I, int j, int q, int NQ) {
-  int rl;
-  const int blk = band_blk(pl, I, j, &rl);
-  return ((size_t)blk * NQ + q) * pl.hpad + rl;
+__host__ __device__ __forceinline__ int sor_lane_pitch(int nop, int rt) { return (rt * ((nop == 2 ? 8 : 5) + 2)) | 1; }
+
+// float4 index of chunk q (0..nq-1 record fields, nq = du, nq+1 = dv) of block (I, j)
+__host__ __device__ __forceinline__ size_t band_f4(const VarRefPlanes& pl, int I, int j, int q) {
+  const int jl = j & ((pl.hpad << pl.rtshift) - 1), rl = jl >> pl.rtshift, s = jl & (pl.rt - 1);
+  return ((size_t)((j >> pl.hbshift) * pl.ndiag + I + rl) * pl.hpad + rl) * pl.lpitch + s * (pl.nq + 2) + q;
 }
 
 // Band plan of a level for the SOR (sor_wave_kernel.cuh).  `rt` rows per lane (tiles of 4 columns x
@@ -107,6 +106,8 @@ inline bool sor_band_plan(int w, int h, int rt, int single_max, int max_cluster,
   pl->hbshift = (hpad == 32 ? 5 : (hpad == 64 ? 6 : (hpad == 128 ? 7 : 8))) + pl->rtshift;
   pl->nb = (lanes + hpad - 1) / hpad;
   pl->ndiag = (w + 3) / 4 + hpad + 2;
+  pl->nq = nop == 2 ? 8 : 5;
+  pl->lpitch = sor_lane_pitch(nop, rt);
   return true;
 }
 

@@ -530,13 +530,18 @@ __global__ void __launch_bounds__(256) patch_p8c1_kernel(LevelGeom g, PatchParam
 // TMA = true is the north-star's variant of the window fill: one lane of the patch issues a tensor
 // tile copy (cp.async.bulk.tensor.3d -> UTMALDG; box = window, coordinates (x*C, y, frame) in a
 // tensor map over the padded I1 frames, out-of-image cells zero-filled by the TMA unit) and the
-// patch's 8 lanes wait on an mbarrier, instead of 8 lanes x ~37 LDG+STS.  It needs the row pitch of
-// the padded image to be a multiple of 16 bytes (tensor-map rule), a box whose inner extent is a
-// multiple of 16 bytes (window rows padded from 17 to 20 floats, RGB 51 to 52) and 128-byte aligned
-// windows; A/B in DESIGN.md section 5 (ofdis_set_option "patch_window_tma").
+// patch's 8 lanes wait on an mbarrier, instead of 8 lanes x ~37 LDG+STS.  Tensor-map rules found the
+// hard way (tools/probe/tma_probe.cu): the row pitch of the padded image must be a multiple of 16
+// bytes (most level widths w+2P are not: only some levels qualify), the box's inner extent too, the
+// window must be 128-byte aligned in shared memory, and -- undocumented, "illegal instruction"
+// otherwise -- the box's START along the inner dimension must be 16-byte aligned as well, i.e. the
+// window's left edge sits on a multiple of 4 pixels and the window grows from 17 to 20 pixels.
+// A/B in DESIGN.md section 5 (ofdis_set_option "patch_window_tma").
+template <int V> struct CostTag { static constexpr int value = V; };
 template <int C> struct PwCfg {
   static constexpr int P = 12, M = 2, W = P + 1 + 2 * M, WC = W * C, PC = P * C, N = P * P * C, NK = N / 8;
-  static constexpr int WCB = (WC + 3) / 4 * 4;  // TMA: window row pitch (floats), inner box extent
+  static constexpr int WT = W + 3;              // TMA: window width (pixels): left edge on a multiple of 4 pixels
+  static constexpr int WCB = WT * C;            // TMA: window row pitch (floats) = inner box extent, a multiple of 4
 };
 template <int NOP, int C, bool TMA> struct PwWin {
   static constexpr int WH = (NOP == 2) ? PwCfg<C>::W : PwCfg<C>::P + 1;          // window rows
@@ -696,11 +701,11 @@ __global__ void __launch_bounds__(256, C == 1 ? 2 : 1) patch_p12_kernel(LevelGeo
         const int tx = pcx + g.pad - P / 2 - 1, ty = pcy + g.pad - P / 2 - 1;
         ux = tx - wx0;
         uy = ty - wy0;
-        restage = (ux < 0) | (ux > 2 * M) | (uy < 0) | (uy > ((NOP == 2) ? 2 * M : 0));
+        restage = (ux < 0) | (ux > 2 * M + (TMA ? 3 : 0)) | (uy < 0) | (uy > ((NOP == 2) ? 2 * M : 0));
         if (restage) {
-          wx0 = tx - M;
+          wx0 = TMA ? ((tx - M) >> 2) << 2 : tx - M;  // TMA: the box must start on a 16-byte boundary
           wy0 = (NOP == 2) ? ty - M : ty;
-          ux = M;
+          ux = tx - wx0;
           uy = (NOP == 2) ? M : 0;
         }
       }
@@ -760,34 +765,43 @@ __global__ void __launch_bounds__(256, C == 1 ? 2 : 1) patch_p12_kernel(LevelGeo
       float m = 0.f;
       if (pp.patnorm > 0) m = fold8(acc, 0.f, true, false) / fn;
       if (active) {
+        // the cost function is uniform over the launch: one copy of the loop per cost instead of a
+        // three-way branch per element (LossComputeErrorImage, patch.cpp:223-262)
+        auto residuals = [&](auto cost_tag) {
+          constexpr int COST = decltype(cost_tag)::value;
 #pragma unroll
-        for (int k = 0; k < NK; ++k) {
-          float d = R[k];
-          if (pp.patnorm > 0) d = d - m;
-          float r, w;
-          if (pp.costfct == 0) {
-            r = d - T[k];
-            w = fabsf(r);
-          } else if (pp.costfct == 1) {
-            const float t = d - T[k];
-            r = copysignf(sqrtf(fabsf(t)), t);
-            w = fabsf(r);
-          } else if (pp.costfct == 2) {
-            const float t = d - T[k];
-            const float hh = sqrtf((sqrtf(1.0f + (t * t) / 25.0f) - 1.0f) * 50.0f);
-            r = copysignf(hh, t);
-            w = fabsf(r);
-          } else {  // reference leaves pdiff/pweight untouched (patch.cpp:230-261)
-            r = d;
-            w = 0.f;
+          for (int k = 0; k < NK; ++k) {
+            float d = R[k];
+            if (pp.patnorm > 0) d = d - m;
+            float r, w;
+            if (COST == 0) {
+              r = d - T[k];
+              w = fabsf(r);
+            } else if (COST == 1) {
+              const float t = d - T[k];
+              r = copysignf(sqrtf(fabsf(t)), t);
+              w = fabsf(r);
+            } else if (COST == 2) {
+              const float t = d - T[k];
+              const float hh = sqrtf((sqrtf(1.0f + (t * t) / 25.0f) - 1.0f) * 50.0f);
+              r = copysignf(hh, t);
+              w = fabsf(r);
+            } else {  // reference leaves pdiff/pweight untouched (patch.cpp:230-261)
+              r = d;
+              w = 0.f;
+            }
+            R[k] = r;
+            const float gx = G_REG ? GX[k] : sGx[k * nthr], gy = G_REG ? GY[k] : sGy[k * nthr];
+            const float vx = gx * r, vy = gy * r;
+            b0 = (k == 0) ? vx : b0 + vx;
+            b1 = (k == 0) ? vy : b1 + vy;
+            sw = (k == 0) ? w : sw + w;
           }
-          R[k] = r;
-          const float gx = G_REG ? GX[k] : sGx[k * nthr], gy = G_REG ? GY[k] : sGy[k * nthr];
-          const float vx = gx * r, vy = gy * r;
-          b0 = (k == 0) ? vx : b0 + vx;
-          b1 = (k == 0) ? vy : b1 + vy;
-          sw = (k == 0) ? w : sw + w;
-        }
+        };
+        if (pp.costfct == 0) residuals(CostTag<0>{});
+        else if (pp.costfct == 1) residuals(CostTag<1>{});
+        else if (pp.costfct == 2) residuals(CostTag<2>{});
+        else residuals(CostTag<3>{});
         wrote_w = (pp.costfct >= 0 && pp.costfct <= 2);
       }
     }
@@ -1044,7 +1058,10 @@ int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     bool tma = false;
-    if (pp.window_tma && ((size_t)g.tmp_w * g.noc * 4) % 16 == 0 && (g.img_fs[3] * 4) % 16 == 0 &&
+    // (RGB flow: 32 windows of 17 x 60 floats + the gradient columns exceed an SM's shared memory: LDG fill)
+    const size_t tma_smem = (size_t)(threads12 / 8) * (((g.nop == 2 ? PwCfg<1>::W : PwCfg<1>::P + 1) * PwCfg<1>::WT * g.noc * 4 + 127) / 128 * 128) +
+                            (g.noc == 1 ? 0 : sizeof(float) * 2 * PwCfg<3>::NK * threads12) + 8 * (threads12 / 8);
+    if (pp.window_tma && tma_smem <= 227 * 1024 && ((size_t)g.tmp_w * g.noc * 4) % 16 == 0 && (g.img_fs[3] * 4) % 16 == 0 &&
         ((uintptr_t)g.img[3]) % 16 == 0) {
       typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -152,15 +152,12 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   const int tid = threadIdx.y * TX + threadIdx.x;
   const int w = g.w, h = g.h, pitch = g.pitch;
   const float* const flow = g.flow + (size_t)frame * g.flow_frame_stride;
-  const float* const dudv = reinterpret_cast<const float*>(pl.dudv + (size_t)fr * pl.dudv_stride);
-  const int hpad = pl.hpad;
-  // float index of du of pixel (x,y) in the band-skewed layout (band_f4 with NQ = 2): float4 0 of a
-  // block holds du x4, float4 1 (4*hpad floats on) dv x4
-  auto dudv_idx = [&pl, hpad](int x, int y) {
-    int rl;
-    const int blk = band_blk(pl, x >> 2, y, &rl);
-    return ((blk * 2) * hpad + rl) * 4 + (x & 3);
-  };
+  float* const rec = reinterpret_cast<float*>(pl.rec + (size_t)fr * pl.rec_stride);
+  const float* const dudv = rec;
+  // float index of field 0 of pixel (x,y) in the band-skewed lane rows (band_f4): chunk f of a block
+  // holds field f of its 4 pixels; du is chunk nq, dv chunk nq+1
+  auto blk_idx = [&pl](int x, int y) { return (int)band_f4(pl, x >> 2, y, 0) * 4 + (x & 3); };
+  const int du_off = pl.nq * 4;
 
   // uu = wx + du (vv likewise); first iteration: uu = wx (refine_variational.cpp:189-190).
   // Coordinates are clamped, which also realises the replicate border of the 3-tap
@@ -173,11 +170,11 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     uv.x = f[0];
     uv.y = (NOP == 2) ? f[1] : 0.0f;
     if (!first) {
-      const int b = dudv_idx(gx, gy);
+      const int b = blk_idx(gx, gy) + du_off;
       const float dx = dudv[b];
       if (NOP == 2) {
         uv.x = uv.x + dx;
-        uv.y = uv.y + dudv[b + 4 * hpad];
+        uv.y = uv.y + dudv[b + 4];
       } else {  // minps / maxps with zero (refine_variational.cpp:299-314)
         const float t = uv.x + dx;
         uv.x = (camlr_of(g, frame) == 0) ? (t < 0.0f ? t : 0.0f) : (t > 0.0f ? t : 0.0f);
@@ -219,8 +216,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   if (i >= w) return;
   const float hdo3 = vp.half_delta_over3, hgo3 = vp.half_gamma_over3;
   const float* const maskp = pl.mask + (size_t)fr * pl.plane;
-  float* const rec = reinterpret_cast<float*>(pl.rec + (size_t)fr * pl.rec_stride);
-  const int fs = hpad * 4;  // floats between consecutive record fields of a block
+  constexpr int fs = 4;  // floats between consecutive record fields of a block
 #pragma unroll 1
   for (int rr = 0; rr < R; ++rr) {
   const int ly = threadIdx.y + TY * rr, j = y0 + ly;
@@ -234,8 +230,20 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
 
   const int o = j * pitch + i;
   const float m = maskp[o];
-  const int db = dudv_idx(i, j);
-  const float u = dudv[db], v = (NOP == 2) ? dudv[db + 4 * hpad] : 0.0f;
+  const int b0 = blk_idx(i, j);
+  // du, dv of this pixel; the first inner iteration starts from zero and resets the stored values (which the
+  // SOR's first sweep reads): refine_variational.cpp:181-182.  The last thread of a row also clears the
+  // columns >= w of the row's last block, which the SOR updates but nobody reads.
+  float u = 0.0f, v = 0.0f;
+  if (first) {
+    rec[b0 + du_off] = 0.0f;
+    rec[b0 + du_off + 4] = 0.0f;
+    if (i == w - 1)
+      for (int t = (i & 3) + 1; t < 4; ++t) rec[b0 + du_off + t - (i & 3)] = rec[b0 + du_off + 4 + t - (i & 3)] = 0.0f;
+  } else {
+    u = dudv[b0 + du_off];
+    v = (NOP == 2) ? dudv[b0 + du_off + 4] : 0.0f;
+  }
   float A11 = 0.f, A12 = 0.f, A22 = 0.f, B1 = 0.f, B2 = 0.f;
 #define DRV(k, c) pl.deriv[k][((size_t)fr * C + (c)) * pl.plane + o]
   if (C == 1) {
@@ -353,8 +361,6 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     const float det = iA11 * iA22 - A12 * A12;
     // record of the 4-pixel block, SoA: float4 f of the block holds field f of its 4 pixels;
     // fields: a11^-1, a12^-1, a22^-1, b1, b2, sh, sv, sv(row above)
-    int rl;
-    const int b0 = ((band_blk(pl, i >> 2, j, &rl) * 8) * hpad + rl) * 4 + (i & 3);  // band_f4(I, j, 0, 8)
     rec[b0] = iA11 / det;
     rec[b0 + fs] = A12 / -det;
     rec[b0 + 2 * fs] = iA22 / det;
@@ -371,8 +377,6 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     if (j < h - 1) sum += vv;
     if (i < w - 1) sum += hh;
     // stereo record fields: A11 = a11 + sum, b1, sh, sv, sv(row above)
-    int rl;
-    const int b0 = ((band_blk(pl, i >> 2, j, &rl) * 5) * hpad + rl) * 4 + (i & 3);  // band_f4(I, j, 0, 5)
     rec[b0] = A11 + sum;
     rec[b0 + fs] = B1;
     rec[b0 + 2 * fs] = hh;
@@ -403,12 +407,12 @@ __global__ void __launch_bounds__(256) flow_update_kernel(LevelGeom g, VarRefPla
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
   const int fr = blockIdx.z, frame = frame_of(g, f0, fr);
   if (i >= g.w || j >= g.h) return;
-  const float* dudv = reinterpret_cast<const float*>(pl.dudv + (size_t)fr * pl.dudv_stride);
-  const size_t b = band_f4(pl, i >> 2, j, 0, 2) * 4 + (i & 3);
+  const float* dudv = reinterpret_cast<const float*>(pl.rec + (size_t)fr * pl.rec_stride);
+  const size_t b = band_f4(pl, i >> 2, j, pl.nq) * 4 + (i & 3);
   float* f = g.flow + (size_t)frame * g.flow_frame_stride + ((size_t)j * g.w + i) * NOP;
   if (NOP == 2) {
     const float2 wv = *reinterpret_cast<const float2*>(f);
-    *reinterpret_cast<float2*>(f) = make_float2(wv.x + dudv[b], wv.y + dudv[b + 4 * pl.hpad]);
+    *reinterpret_cast<float2*>(f) = make_float2(wv.x + dudv[b], wv.y + dudv[b + 4]);
   } else {
     const float t = f[0] + dudv[b];
     f[0] = (camlr_of(g, frame) == 0) ? (t < 0.0f ? t : 0.0f) : (t > 0.0f ? t : 0.0f);
@@ -497,7 +501,6 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
     warp_kernel<C, NOP><<<grid, block, 0, st>>>(g, pl, f0);
     deriv1_kernel<C><<<gridc, block, 0, st>>>(g, pl);
     deriv2_kernel<C><<<gridc, block, 0, st>>>(g, pl);
-    cudaMemsetAsync(pl.dudv, 0, sizeof(float4) * pl.dudv_stride * nf, st);
   }
   launches += 3;
   // SOR: band plan of the level (pl.hpad rows per band, pl.nb bands == CTAs of a cluster) and as

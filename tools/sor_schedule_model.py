@@ -7,13 +7,13 @@ still be in flight.  RT = rows per lane (tile of 4 columns x RT rows per thread 
 CPU-only; python tools/sor_schedule_model.py [W4 h HPAD RT K]."""
 import sys
 
-PF = 3
+PF = 4
 
 
 def run(W4, h, HPAD, RT, K, verbose=False):
     HB = HPAD * RT
     nb = (h + HB - 1) // HB
-    NR = 2 * K + PF
+    NR = PF + 1 if K == 1 else PF + 2 * K - 1   # sor_stages
     R = (h + RT - 1) // RT
     S = W4 + R + 2 * K - 2
     glob = {(I, j): -1 for I in range(W4) for j in range(h)}  # sweep whose value is stored; -1 = before this solve
@@ -44,20 +44,20 @@ def run(W4, h, HPAD, RT, K, verbose=False):
         for t in ctas:
             tl = T - t.r0
             n = tl + PF
-            if 0 <= n < t.S_loc:  # producer
-                d1 = min(n + 1, t.dmax)
-                ih = min(max(n - (HPAD - 1), 0), W4 - 1)
+            if 0 <= n < t.S_loc:  # producer: the occupied lane rows of diagonal n (records and du,dv) + the halo block
+                ih = min(max(n - HPAD, 0), W4 - 1)
                 snap = {}
-                for rl in range(t.nl):
-                    I = d1 - rl
-                    for s in range(RT):
-                        j = t.j0 + rl * RT + s
-                        if 0 <= I < W4 and j < h:
-                            snap[("dud", rl, s)] = ((I, j), glob[(I, j)])
+                if n <= t.dmax:
+                    for rl in range(max(0, n - (W4 - 1)), min(t.nl - 1, n) + 1):
+                        I = n - rl
+                        for s in range(RT):
+                            j = t.j0 + rl * RT + s
+                            if j < h:
+                                snap[("dud", rl, s)] = ((I, j), glob[(I, j)])
                 if t.c + 1 < nb:
                     snap["halo"] = ((ih, t.j0 + HB), glob[(ih, t.j0 + HB)])
-                t.stage[t.ist] = dict(n=n, rec_d=min(n, t.dmax), dud_d=d1, halo_I=ih, snap=snap, issued=T)
-                pending.append((t, t.ist, t.r0 + n - 1))
+                t.stage[t.ist] = dict(n=n, rec_d=n, halo_I=ih, snap=snap, issued=T)
+                pending.append((t, t.ist, t.r0 + n - 2))  # waited for two super-steps before sweep 0's tile on it
                 t.ist = (t.ist + 1) % NR
             for (k, rl), th in t.thr.items():
                 n = tl - 2 * k
@@ -70,6 +70,7 @@ def run(W4, h, HPAD, RT, K, verbose=False):
                     st = t.stage[th["st"]]
                     if in_range:
                         assert st is not None and st["n"] == n and st["rec_d"] == I + rl and st["issued"] < T
+                        assert ("dud", rl, 0) in st["snap"], "lane row inside the trimmed copy"
                     own = list(th["own"])
                     rf = [None] * RT
                     nxt = [None] * RT
@@ -79,23 +80,22 @@ def run(W4, h, HPAD, RT, K, verbose=False):
                                 j = t.j0 + rl * RT + s
                                 if j >= h:
                                     continue
-                                if n >= 1:
-                                    sp = t.stage[th["stp"]]
-                                    assert sp["n"] == n - 1 and sp["dud_d"] == n
-                                    own[s] = sp["snap"][("dud", rl, s)]
-                                else:
-                                    own[s] = ((I, j), glob[(I, j)])
+                                own[s] = st["snap"][("dud", rl, s)]
                                 assert own[s] == ((I, j), -1), ("own", own[s])
-                                if I + 1 < W4:
-                                    assert st["dud_d"] == n + 1
-                                    assert st["snap"][("dud", rl, s)] == ((I + 1, j), -1)
+                            sb = t.stage[(th["st"] + 1) % NR]  # diagonal n+1: right and bottom neighbours
                             jb = t.j0 + rl * RT + RT  # row below the tile
+                            if I + 1 < W4 or jb < h:
+                                assert sb is not None and sb["n"] == n + 1 and t.r0 + n + 1 - 2 <= T - 1, "load n+1 landed"
+                            for s in range(RT):
+                                j = t.j0 + rl * RT + s
+                                if j < h and I + 1 < W4:
+                                    assert sb["snap"][("dud", rl, s)] == ((I + 1, j), -1)
                             if jb < h:
                                 if rl + 1 < HPAD:
-                                    bot = st["snap"][("dud", rl + 1, 0)]
+                                    bot = sb["snap"][("dud", rl + 1, 0)]
                                 else:
-                                    assert st["halo_I"] == I
-                                    bot = st["snap"]["halo"]
+                                    assert sb["halo_I"] == I
+                                    bot = sb["snap"]["halo"]
                                 assert bot == ((I, jb), -1), ("bot k0", bot, I, jb)
                     else:
                         for s in range(RT):
