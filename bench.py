@@ -600,7 +600,7 @@ def main():
             tj = json.load(open(tp))
             traffic = tj.get("sor_dram_bytes_per_launch")
             # what actually bounds the overlapped step: warp-instruction issue.  ncu counts the warp
-            # instructions of one step (profiles/r1c_launches_step_b64.csv); an SM issues at most
+            # instructions of one step (profiles/r2_launches_step_b64.csv); an SM issues at most
             # 4 per cycle.  Utilisation = instructions / (step time x SMs x 4 x SM clock).
             wi = tj.get("warp_instructions_per_step")
             if wi and B == 64 and clocks.get("sm_mhz"):
@@ -609,8 +609,9 @@ def main():
                          "issue_slot_utilisation": wi / (ms_res * 1e-3 * sms * 4 * clocks["sm_mhz"] * 1e6),
                          "ipc_per_sm": wi / (ms_res * 1e-3 * sms * clocks["sm_mhz"] * 1e6)}
         roof = {"bound": "hbm", "kernel": "sor_wave_kernel (lexicographic SOR wavefront, all sweeps fused, one CTA per frame at this level size)", "achieved": ach,
-                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_note": "ncu dram bytes per SOR launch with caches flushed before every replay; "
-                "2.99e6 with --cache-control none (profiles/roofline_traffic.json)", "issue": issue, "peak_source": how,
+                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_note": "ncu dram bytes per SOR launch with caches flushed before every replay (1.04x the "
+                "algorithmic bytes); 0.32e6 with --cache-control none, i.e. behind assemble_kernel in the level loop "
+                "(profiles/roofline_traffic.json)", "issue": issue, "peak_source": how,
                 "algorithmic_bytes_per_step": alg, "kernel_ms_per_step": sor["ms_per_step"],
                 "launches_per_step": sor["launches_per_step"],
                 "share_of_step": {k: v["ms_per_step"] for k, v in prof.items()}}

@@ -192,7 +192,10 @@ int ofdis_profile_levels(ofdis_ctx* ctx, int nframes, int steps, double* ms_by_c
  * forward one".  This is what two stand-alone PatGridClass objects joined by SetComplGrid
  * (patchgrid.h:36, oflow.cpp:162-170) are built on. */
 int ofdis_set_direction(ofdis_ctx* ctx, int dir);
-/* Launch-geometry options (tuning / test hook, results are bit-identical under every setting):
+/* Options.  "sor_fast" 0 (default) | 1 switches the refinement's solver from the reference's lexicographic SOR to a
+ *   red-black SOR (same system, omega and sweep count): NOT bit-identical to the reference --
+ *   the flow differs by a few hundredths of a pixel (bench.py reports the delta) -- and never covered by the parity
+ *   claim.  All other options are launch geometry (tuning / test hook), results are bit-identical under every setting:
  *   "sor_rows_per_thread" 1 (default for flow) | 2 (default for stereo) | 4: rows of the 4-column tile one SOR thread updates per super-step
  *                     (a level needs W/4 + h/rows super-steps; sor_wave_kernel.cuh)
  *   "sor_single_max"  32 | 64 | 128 (default): refinement levels of up to this many SOR lanes (= rows / rows per

@@ -48,6 +48,8 @@ struct ofdis_ctx {
   std::vector<size_t> flow_floats;
   VarRefPlanes planes{};
   float* d_planes = nullptr;
+  float* d_fast = nullptr;          // fast-mode records and (du,dv) ping-pong planes (ofdis_set_option "sor_fast")
+  int last_vr_fcur = 0;
   PatchParams pp{};
   long launches = 0;
   int last_vr_level = -1, last_vr_f0 = 0;
@@ -349,6 +351,7 @@ int ofdis_destroy(ofdis_ctx* ctx) {
     cudaFree(L.fb_reach);
   }
   cudaFree(ctx->d_planes);
+  cudaFree(ctx->d_fast);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return OFDIS_OK;
@@ -647,6 +650,8 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   if (!sor_band_plan(L->w, L->h, ctx->sor_rt, ctx->sor_single_max, ctx->sor_max_cluster, ctx->nop, ctx->prm.tv_solverit, &pl))
     return fail(ctx, OFDIS_ERR_UNSUPPORTED, "varref_refine: level too tall for the largest SOR cluster");
   pl.rec_stride = (size_t)pl.nb * pl.ndiag * pl.hpad * pl.lpitch;
+  pl.frec_stride = pl.plane * 8;   // fast mode: natural layout at this level's plane size
+  pl.fdu_stride = pl.plane * 4;
   // usefbcon: both directions are refined except on the last level (oflow.cpp:285-294)
   const int D = ctx->dirs;
   const bool fwd_only = (D == 2 && level == ctx->prm.sc_l);
@@ -655,6 +660,7 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "varref kernels launch", cudaGetLastError());
   ctx->launches += n;
   ctx->last_vr_level = level;
+  ctx->last_vr_fcur = vp.n_inner & 1;
   ctx->last_vr_f0 = f0;
   ctx->last_vr_fstep = fwd_only ? 1 : D;  // workspace slots per user frame
   return OFDIS_OK;
@@ -684,6 +690,21 @@ int ofdis_set_option(ofdis_ctx* ctx, const char* name, int value) {
     if (ctx->prm.usetvref && !sor_band_plan(ctx->lev[0].w, ctx->lev[0].h, ctx->sor_rt, 128, value, ctx->nop, ctx->prm.tv_solverit, &probe))
       return fail(ctx, OFDIS_ERR_UNSUPPORTED, "sor_max_cluster: the finest level needs the larger cluster");
     ctx->sor_max_cluster = value;
+  } else if (!strcmp(name, "sor_fast")) {
+    if (value != 0 && value != 1) return fail(ctx, OFDIS_ERR_ARG, "sor_fast: 0 or 1");
+    if (!ctx->d_planes) return fail(ctx, OFDIS_ERR_ARG, "sor_fast: context created with usetvref=0");
+    if (value && rb_smem_limit_exceeded(ctx->nop, ctx->prm.tv_solverit))
+      return fail(ctx, OFDIS_ERR_UNSUPPORTED, "sor_fast: too many sweeps for the tile's halo");
+    if (value && !ctx->d_fast) {  // records 8 floats per pixel + 2 x 2 planes of (du,dv), finest level x frames
+      const size_t plane = ctx->planes.plane;
+      CK(cudaSetDevice(ctx->device));
+      if (cudaMalloc((void**)&ctx->d_fast, sizeof(float) * plane * 12 * ctx->cap) != cudaSuccess)
+        return fail(ctx, OFDIS_ERR_NOMEM, "sor_fast workspace");
+      cudaMemsetAsync(ctx->d_fast, 0, sizeof(float) * plane * 12 * ctx->cap, ctx->stream);
+      ctx->planes.frec = ctx->d_fast;
+      ctx->planes.fdu = ctx->d_fast + plane * 8 * ctx->cap;
+    }
+    ctx->planes.fast = value;
   } else if (!strcmp(name, "patch_window_tma")) {
     if (value != 0 && value != 1) return fail(ctx, OFDIS_ERR_ARG, "patch_window_tma: 0 or 1");
     ctx->pp.window_tma = value;
@@ -813,6 +834,18 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
   if (!strcmp(name, "dudv") || !strcmp(name, "rec")) {
     // stored skewed (see VarRefPlanes); returned in natural (h, pitch, per-pixel) order
     const bool is_rec = name[0] == 'r';
+    if (ctx->planes.fast) {  // natural layout: records 8 floats per pixel, (du,dv) two planes of the current buffer
+      const int per_f = is_rec ? (L->nop == 2 ? 8 : 5) : 2;
+      if (plane * per_f > max_floats) return OFDIS_ERR_ARG;
+      std::vector<float> raw(is_rec ? plane * 8 : plane * 2);
+      const float* src_f = is_rec ? ctx->planes.frec + (size_t)fr * plane * 8
+                                  : ctx->planes.fdu + (size_t)fr * plane * 4 + (size_t)ctx->last_vr_fcur * 2 * plane;
+      if (cudaMemcpyAsync(raw.data(), src_f, sizeof(float) * raw.size(), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return OFDIS_ERR_CUDA;
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return OFDIS_ERR_CUDA;
+      for (size_t o = 0; o < plane; ++o)
+        for (int e = 0; e < per_f; ++e) dst[o * per_f + e] = is_rec ? raw[o * 8 + e] : raw[(size_t)e * plane + o];
+      return (long)(plane * per_f);
+    }
     VarRefPlanes bp{};
     if (!sor_band_plan(L->w, L->h, ctx->sor_rt, ctx->sor_single_max, ctx->sor_max_cluster, ctx->nop, ctx->prm.tv_solverit, &bp)) return OFDIS_ERR_UNSUPPORTED;
     const int per = is_rec ? bp.nq : 2;                              // floats per pixel

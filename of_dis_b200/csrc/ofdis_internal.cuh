@@ -72,6 +72,14 @@ struct VarRefPlanes {
   int ndiag;               // diagonals stored per band: W4 + hpad + 2
   int nq;                  // record fields per block: 8 (flow) / 5 (stereo); chunk nq = du, nq+1 = dv
   int lpitch;              // float4 per lane row: rt*(nq+2), made odd
+  // "Fast" refinement (ofdis_set_option "sor_fast"; NOT bit-exact): red-black
+  // SOR on natural-layout arrays -- records [frames][h][pitch][8] (a11^-1 a12^-1 a22^-1 b1 b2 sh sv -; stereo
+  // A11 b1 sh sv), (du,dv) as two ping-pong buffers of two planes each [frames][2][2][h*pitch].
+  int fast;                // 0 = exact lexicographic SOR (default)
+  int fcur;                // ping-pong buffer that holds the current (du,dv)
+  float* frec;
+  float* fdu;
+  size_t frec_stride, fdu_stride;  // floats per frame
 };
 
 __host__ __device__ __forceinline__ int sor_lane_pitch(int nop, int rt) { return (rt * ((nop == 2 ? 8 : 5) + 2)) | 1; }
@@ -165,6 +173,8 @@ int launch_flow_upsample(const LevelGeom& g, int f0, int f1, float* out, int w_o
 int launch_varref(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
                   cudaStream_t st, Profiler* prof = nullptr);
 
+// fast mode: does the red-black kernel's staged tile (32 + 4K pixels square) exceed an SM's shared memory?
+bool rb_smem_limit_exceeded(int nop, int K);
 // largest thread-block cluster the SOR kernel can be launched with on the current device (8 or 16)
 int sor_max_cluster_size();
 

@@ -152,12 +152,16 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   const int tid = threadIdx.y * TX + threadIdx.x;
   const int w = g.w, h = g.h, pitch = g.pitch;
   const float* const flow = g.flow + (size_t)frame * g.flow_frame_stride;
-  float* const rec = reinterpret_cast<float*>(pl.rec + (size_t)fr * pl.rec_stride);
-  const float* const dudv = rec;
-  // float index of field 0 of pixel (x,y) in the band-skewed lane rows (band_f4): chunk f of a block
-  // holds field f of its 4 pixels; du is chunk nq, dv chunk nq+1
-  auto blk_idx = [&pl](int x, int y) { return (int)band_f4(pl, x >> 2, y, 0) * 4 + (x & 3); };
-  const int du_off = pl.nq * 4;
+  // Records and (du,dv) of pixel (x,y).  Exact mode: the band-skewed lane rows (band_f4): chunk f of a
+  // block holds field f of its 4 pixels, du is chunk nq, dv chunk nq+1.  Fast mode (red-black SOR):
+  // natural layout, 8 floats per pixel, (du,dv) in the current ping-pong planes.
+  const bool fast = pl.fast != 0;
+  float* const rec = fast ? pl.frec + (size_t)fr * pl.frec_stride : reinterpret_cast<float*>(pl.rec + (size_t)fr * pl.rec_stride);
+  float* const dudv = fast ? pl.fdu + (size_t)fr * pl.fdu_stride + (size_t)pl.fcur * 2 * pl.plane : rec;
+  const int fs = fast ? 1 : 4;                       // floats between consecutive record fields of a pixel
+  const int dv_off = fast ? (int)pl.plane : 4;       // from du to dv
+  auto rec_idx = [&pl, fast, pitch](int x, int y) { return fast ? (y * pitch + x) * 8 : (int)band_f4(pl, x >> 2, y, 0) * 4 + (x & 3); };
+  auto du_idx = [&pl, fast, pitch](int x, int y) { return fast ? y * pitch + x : (int)band_f4(pl, x >> 2, y, pl.nq) * 4 + (x & 3); };
 
   // uu = wx + du (vv likewise); first iteration: uu = wx (refine_variational.cpp:189-190).
   // Coordinates are clamped, which also realises the replicate border of the 3-tap
@@ -170,11 +174,11 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     uv.x = f[0];
     uv.y = (NOP == 2) ? f[1] : 0.0f;
     if (!first) {
-      const int b = blk_idx(gx, gy) + du_off;
+      const int b = du_idx(gx, gy);
       const float dx = dudv[b];
       if (NOP == 2) {
         uv.x = uv.x + dx;
-        uv.y = uv.y + dudv[b + 4];
+        uv.y = uv.y + dudv[b + dv_off];
       } else {  // minps / maxps with zero (refine_variational.cpp:299-314)
         const float t = uv.x + dx;
         uv.x = (camlr_of(g, frame) == 0) ? (t < 0.0f ? t : 0.0f) : (t > 0.0f ? t : 0.0f);
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   if (i >= w) return;
   const float hdo3 = vp.half_delta_over3, hgo3 = vp.half_gamma_over3;
   const float* const maskp = pl.mask + (size_t)fr * pl.plane;
-  constexpr int fs = 4;  // floats between consecutive record fields of a block
+
 #pragma unroll 1
   for (int rr = 0; rr < R; ++rr) {
   const int ly = threadIdx.y + TY * rr, j = y0 + ly;
@@ -230,19 +234,19 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
 
   const int o = j * pitch + i;
   const float m = maskp[o];
-  const int b0 = blk_idx(i, j);
+  const int b0 = rec_idx(i, j), bd = du_idx(i, j);
   // du, dv of this pixel; the first inner iteration starts from zero and resets the stored values (which the
   // SOR's first sweep reads): refine_variational.cpp:181-182.  The last thread of a row also clears the
-  // columns >= w of the row's last block, which the SOR updates but nobody reads.
+  // columns >= w of the row's last block, which the exact SOR updates but nobody reads.
   float u = 0.0f, v = 0.0f;
   if (first) {
-    rec[b0 + du_off] = 0.0f;
-    rec[b0 + du_off + 4] = 0.0f;
-    if (i == w - 1)
-      for (int t = (i & 3) + 1; t < 4; ++t) rec[b0 + du_off + t - (i & 3)] = rec[b0 + du_off + 4 + t - (i & 3)] = 0.0f;
+    dudv[bd] = 0.0f;
+    dudv[bd + dv_off] = 0.0f;
+    if (!fast && i == w - 1)
+      for (int t = (i & 3) + 1; t < 4; ++t) dudv[bd + t - (i & 3)] = dudv[bd + 4 + t - (i & 3)] = 0.0f;
   } else {
-    u = dudv[b0 + du_off];
-    v = (NOP == 2) ? dudv[b0 + du_off + 4] : 0.0f;
+    u = dudv[bd];
+    v = (NOP == 2) ? dudv[bd + dv_off] : 0.0f;
   }
   float A11 = 0.f, A12 = 0.f, A22 = 0.f, B1 = 0.f, B2 = 0.f;
 #define DRV(k, c) pl.deriv[k][((size_t)fr * C + (c)) * pl.plane + o]
@@ -398,6 +402,7 @@ __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
 }
 
 #include "sor_wave_kernel.cuh"
+#include "sor_redblack_kernel.cuh"
 
 // K12 at the end of the level: flow = w + dw (refine_variational.cpp:210-221; stereo clamp
 // :299-314).  Kept out of the SOR kernel: the flow array is row-major per frame, so reading it
@@ -407,12 +412,15 @@ __global__ void __launch_bounds__(256) flow_update_kernel(LevelGeom g, VarRefPla
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
   const int fr = blockIdx.z, frame = frame_of(g, f0, fr);
   if (i >= g.w || j >= g.h) return;
-  const float* dudv = reinterpret_cast<const float*>(pl.rec + (size_t)fr * pl.rec_stride);
-  const size_t b = band_f4(pl, i >> 2, j, pl.nq) * 4 + (i & 3);
+  const bool fast = pl.fast != 0;
+  const float* dudv = fast ? pl.fdu + (size_t)fr * pl.fdu_stride + (size_t)pl.fcur * 2 * pl.plane
+                           : reinterpret_cast<const float*>(pl.rec + (size_t)fr * pl.rec_stride);
+  const size_t b = fast ? (size_t)j * g.pitch + i : band_f4(pl, i >> 2, j, pl.nq) * 4 + (i & 3);
+  const size_t dv_off = fast ? pl.plane : 4;
   float* f = g.flow + (size_t)frame * g.flow_frame_stride + ((size_t)j * g.w + i) * NOP;
   if (NOP == 2) {
     const float2 wv = *reinterpret_cast<const float2*>(f);
-    *reinterpret_cast<float2*>(f) = make_float2(wv.x + dudv[b], wv.y + dudv[b + 4]);
+    *reinterpret_cast<float2*>(f) = make_float2(wv.x + dudv[b], wv.y + dudv[b + dv_off]);
   } else {
     const float t = f[0] + dudv[b];
     f[0] = (camlr_of(g, frame) == 0) ? (t < 0.0f ? t : 0.0f) : (t > 0.0f ? t : 0.0f);
@@ -485,8 +493,10 @@ static cudaError_t launch_sor(const LevelGeom& g, const VarRefPlanes& pl, const 
 }
 
 template <int C, int NOP>
-static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams& vp, int f0, int f1,
+static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl_in, const VarRefParams& vp, int f0, int f1,
                            cudaStream_t st, Profiler* prof) {
+  VarRefPlanes pl = pl_in;  // fast mode toggles the (du,dv) ping-pong buffer
+  pl.fcur = 0;
   int launches = 0;
   const int nf = f1 - f0;
   const dim3 block(TX, TY), grid((g.w + TX - 1) / TX, (g.h + TY - 1) / TY, nf);
@@ -516,6 +526,23 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl, const Var
       else assemble_kernel<C, NOP, 1><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
     }
     ++launches;
+    if (pl.fast) {  // opt-in red-black solver: all K sweeps in one launch, (du,dv) ping-pong
+      ProfScope scope(prof, KC_VR_SOR);
+      const size_t smem = rb_smem_bytes(NOP, K);
+      if (K < 1 || smem > 227 * 1024) return -1;
+      static size_t smem_set[64] = {0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev >= 0 && dev < 64 && smem_set[dev] < smem) {
+        if (cudaFuncSetAttribute(sor_redblack_kernel<NOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        smem_set[dev] = smem;
+      }
+      const dim3 grid_rb((g.w + RB_TILE - 1) / RB_TILE, (g.h + RB_TILE - 1) / RB_TILE, nf);
+      sor_redblack_kernel<NOP><<<grid_rb, 256, smem, st>>>(g, pl, vp);
+      pl.fcur ^= 1;
+      ++launches;
+      continue;
+    }
     for (int s = 0; s < K; s += kl) {
       ProfScope scope(prof, KC_VR_SOR);
       if (launch_sor<NOP>(g, pl, vp, nf, (K - s < kl) ? K - s : kl, st) != cudaSuccess) return -1;
@@ -535,6 +562,8 @@ extern "C" int ofdis_debug_sor_times(long long* dst) {
   return cudaMemcpyFromSymbol(dst, g_sor_times, sizeof(g_sor_times)) == cudaSuccess ? 0 : -1;
 }
 #endif
+
+bool rb_smem_limit_exceeded(int nop, int K) { return K < 1 || rb_smem_bytes(nop, K) > 227 * 1024; }
 
 bool sor_fits(int nop, int hpad, int rt, int K) {
   return K * hpad + 32 <= sor_max_threads(hpad) && sor_smem_bytes(nop, hpad, rt, K) <= 227 * 1024;
