@@ -21,6 +21,7 @@ per pair.
           pyramids/finest results are checked bit for bit against the resident path
   sharded : BASELINE configs[3] as written -- 64 pairs TOTAL owned by rank 0, scattered over the ranks'
           GPUs with NCCL, gathered back (strong scaling; of_dis_b200/sharding.py)
+  fast_mode : the opt-in red-black refinement (not bit-identical; throughput, delta to the exact flow, EPE of both)
   big_configs : BASELINE configs[2] and [4] (1920x1080 RGB, 2880x1988 stereo) on one GPU, per kernel class
   single_lane / batch_sweep : one lane, L2 flushed before every step (latency of 64, 8, 1 pairs)
   roofline     : dominant kernel (lexicographic SOR), algorithmic bytes / CUDA-event time, plus the
@@ -644,6 +645,59 @@ def main():
             sweep[str(b)] = {"ms_per_step": ms, "value": b * H_ORG * W_ORG / (ms * 1e-3) / 1e6,
                              "e2e_ms_per_step": ms2, "e2e_value": b * H_ORG * W_ORG / (ms2 * 1e-3) / 1e6}
             c2.close()
+            if not args.no_extras:  # the same latency with the opt-in red-black refinement (see fast_mode)
+                c3 = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, b, device=local,
+                                 stream=stream.cuda_stream)
+                c3.set_option("sor_fast", 1)
+                c3.upload_packed(0, b, host_in.data_ptr())
+                c3.set_graph_mode(True)
+                for _ in range(3):
+                    c3.run(b)
+                sweep[str(b)]["fast_mode_ms_per_step"] = timed(lambda: c3.run(b), 10)
+                c3.close()
+
+    # ---- opt-in red-black refinement (ofdis_set_option "sor_fast"; NOT the reference's iterate) ----
+    fast = None
+    if world == 1 and not args.no_extras:
+        try:
+            from of_dis_b200 import synth as _synth
+            fl = []
+            for l in lanes:
+                c = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, B, device=local, stream=l[1].cuda_stream)
+                c.set_option("sor_fast", 1)
+                c.upload_packed(0, B, host_in.data_ptr())
+                c.set_graph_mode(True)
+                fl.append(c)
+            for i in range(NL * args.warmup):
+                fl[i % NL].run(B)
+            barrier()
+            ms_fast = pipelined(lambda i: fl[i % NL].run(B), args.steps)
+            ms_fast_single = timed(lambda: fl[0].run(B), args.steps)
+            fast_flow = torch.empty((B, flow_floats), dtype=torch.float32)
+            fl[0].get_flow_batch(0, B, fast_flow.data_ptr())
+            fl[0].sync()
+            gu, gv = _synth.synthetic_flow(H_ORG, W_ORG, 6.0, False)
+            gt = np.stack([gu, gv], -1).astype(np.float32)
+            n_chk = min(B, MAX_DISTINCT)
+            epe = {"exact": [], "fast": []}
+            dlt = []
+            for f in range(n_chk):
+                full = {}
+                for key, src in (("exact", resident_flow), ("fast", fast_flow)):
+                    full[key] = _pp.postprocess(src[f].numpy().reshape(li["h"], li["w"], prm.nop), prm.sc_l, pyrs[0].padw,
+                                                pyrs[0].padh, W_ORG, H_ORG)
+                    epe[key].append(float(np.sqrt(((full[key] - gt) ** 2).sum(-1)).mean()))
+                dlt.append(float(np.abs(full["exact"] - full["fast"]).mean()))
+            for c in fl:
+                c.close()
+            fast = {"value": pix / (ms_fast * 1e-3) / 1e6, "ms_per_step": ms_fast, "unit": "Mpix/s",
+                    "single_lane_ms_per_step": ms_fast_single,
+                    "mean_abs_delta_px": float(np.mean(dlt)), "epe_exact_px": float(np.mean(epe["exact"])),
+                    "epe_fast_px": float(np.mean(epe["fast"])), "pairs_checked": n_chk,
+                    "note": "same linear systems, red-black instead of lexicographic sweep order: not bit-identical to the "
+                            "reference and excluded from every parity claim and from value/e2e above; deltas at full resolution"}
+        except Exception as e:
+            fast = {"error": str(e)}
 
     numa.unbind(prev_affinity)  # the CPU baseline uses every core of the host
     cores = os.cpu_count() or 1
@@ -668,7 +722,7 @@ def main():
                         "note": "one context, one stream, L2 flushed before every step"},
         "e2e": lead,
         "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
-        "clocks": clocks, "roofline": roof, "batch_sweep": sweep, "sharded": sharded, "big_configs": big,
+        "clocks": clocks, "roofline": roof, "batch_sweep": sweep, "sharded": sharded, "big_configs": big, "fast_mode": fast,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu

@@ -397,6 +397,27 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// predicated forms: lanes without a block issue no shared-memory wavefronts.  The result registers of such a
+// lane keep whatever they held (no zero-fill: 44 CS2R per super-step); its arithmetic runs on that garbage and
+// is never stored, and no branch of the kernel depends on data of a lane without a block.
+__device__ __forceinline__ float4 lds128_if(bool p, unsigned addr) {
+  float4 v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr), "r"((unsigned)p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32_if(bool p, unsigned addr) {
+  float v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.shared.f32 %0, [%1];\n\t}" : "=f"(v) : "r"(addr), "r"((unsigned)p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128_if(bool p, unsigned addr, const float4& v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n\t}" ::"r"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "r"((unsigned)p)
+               : "memory");
+}
 __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }

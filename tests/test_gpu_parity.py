@@ -178,6 +178,29 @@ def test_batch_of_frames_and_graph_replay(api, oracle_port):
     ctx.close()
 
 
+def test_bench_batch_of_64_pairs_vs_oracle(api, oracle_port):
+    """The bench workload itself (bench.py: 64 pairs per launch, 16 distinct, graph replay): every frame of the batch
+    equals the oracle's flow of its pair -- six distinct pairs against the oracle, all 64 slots against those."""
+    prm = params.operating_point(2, 1024)
+    nfr, ndist = 64, 16
+    pyrs = []
+    for s in range(ndist):
+        i0, i1, _ = synth.synthetic_pair(436, 1024, 1, seed=s)
+        pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
+    ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, nfr)
+    packed = np.stack([ctx.pack_frame(pyrs[f % ndist]) for f in range(nfr)])
+    ctx.upload_packed(0, nfr, packed)
+    ctx.set_graph_mode(True)
+    ctx.run(nfr)
+    ctx.run(nfr)
+    flows = [ctx.get_flow(f, prm.sc_l) for f in range(nfr)]
+    ctx.close()
+    for d in (0, 3, 6, 9, 12, 15):
+        assert_bits(flows[d], oracle_port.port_run(pyrs[d], prm), "pair %d" % d)
+    for f in range(nfr):
+        assert_bits(flows[f], flows[f % ndist], "slot %d" % f)
+
+
 def test_properties_at_full_size(api):
     """Size-independent properties at BASELINE cfg 2 size: identical images -> exactly zero flow;
     the reference-shaped OFClass wrapper gives the same result as the batch engine."""
