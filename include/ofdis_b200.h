@@ -196,6 +196,9 @@ int ofdis_set_direction(ofdis_ctx* ctx, int dir);
  *   red-black SOR (same system, omega and sweep count): NOT bit-identical to the reference --
  *   the flow differs by a few hundredths of a pixel (bench.py reports the delta) -- and never covered by the parity
  *   claim.  All other options are launch geometry (tuning / test hook), results are bit-identical under every setting:
+ *   "sor_lane"        1 (default) | 0: refinement levels of few 32-row bands (<= 16 warps of bands x sweeps, within the
+ *                     shared memory of an SM: up to 128 rows at 3 sweeps) run the SOR as a pixel wavefront whose warps
+ *                     synchronise through shared-memory flags (sor_lane_kernel.cuh); 0 = the block wavefront everywhere
  *   "sor_rows_per_thread" 1 (default for flow) | 2 (default for stereo) | 4: rows of the 4-column tile one SOR thread updates per super-step
  *                     (a level needs W/4 + h/rows super-steps; sor_wave_kernel.cuh)
  *   "sor_single_max"  32 | 64 | 128 (default): refinement levels of up to this many SOR lanes (= rows / rows per

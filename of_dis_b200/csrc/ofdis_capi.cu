@@ -32,6 +32,7 @@ struct ofdis_ctx {
   // SOR band plan (sor_band_plan): levels of up to sor_single_max rows run in one CTA, taller ones in a
   // cluster of up to sor_max_cluster CTAs (8 = portable limit; 16 where the device grants it)
   int sor_single_max = 128, sor_max_cluster = 8, sor_dev_cluster = 8, sor_rt = 1;  // defaults set in ofdis_create
+  int sor_lane = 1;  // levels of few 32-row bands: pixel wavefront (sor_lane_kernel) instead of the block wavefront
   int nlev = 0;                    // sc_f - sc_l + 1
   std::vector<LevelGeom> lev;      // index: level - sc_l
   std::vector<size_t> img_off;     // [lev][4] offsets (floats) inside one packed frame
@@ -310,6 +311,8 @@ int ofdis_create(ofdis_ctx** out, int device, void* stream, const ofdis_params* 
             if (sor_band_plan(L.w, L.h, rt, sm, mc, nop, prm->tv_solverit, &t))
               recf4 = std::max(recf4, (size_t)t.nb * t.ndiag * t.hpad * t.lpitch);
           }
+    for (const LevelGeom& L : ctx->lev)  // lane mode (sor_lane_kernel) of the levels it can take
+      if (sor_lane_fits(L.h, 1)) recf4 = std::max(recf4, lane_frame_f4(L.w, L.h));
     const size_t per_frame = plane * (1 + C + 8 * C) + recf4 * 4;
     ok = dalloc((void**)&ctx->d_planes, sizeof(float) * per_frame * cap);
     if (ok) {
@@ -650,6 +653,13 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   if (!sor_band_plan(L->w, L->h, ctx->sor_rt, ctx->sor_single_max, ctx->sor_max_cluster, ctx->nop, ctx->prm.tv_solverit, &pl))
     return fail(ctx, OFDIS_ERR_UNSUPPORTED, "varref_refine: level too tall for the largest SOR cluster");
   pl.rec_stride = (size_t)pl.nb * pl.ndiag * pl.hpad * pl.lpitch;
+  pl.lane = 0;
+  if (ctx->sor_lane && !pl.fast && sor_lane_fits(L->h, 1)) {  // lane-skewed layout, bands of 32 rows
+    pl.lane = 1;
+    pl.nb = (L->h + 31) / 32;
+    pl.ndiag = L->w + 32;
+    pl.rec_stride = lane_frame_f4(L->w, L->h);
+  }
   pl.frec_stride = pl.plane * 8;   // fast mode: natural layout at this level's plane size
   pl.fdu_stride = pl.plane * 4;
   // usefbcon: both directions are refined except on the last level (oflow.cpp:285-294)
@@ -690,6 +700,9 @@ int ofdis_set_option(ofdis_ctx* ctx, const char* name, int value) {
     if (ctx->prm.usetvref && !sor_band_plan(ctx->lev[0].w, ctx->lev[0].h, ctx->sor_rt, 128, value, ctx->nop, ctx->prm.tv_solverit, &probe))
       return fail(ctx, OFDIS_ERR_UNSUPPORTED, "sor_max_cluster: the finest level needs the larger cluster");
     ctx->sor_max_cluster = value;
+  } else if (!strcmp(name, "sor_lane")) {
+    if (value != 0 && value != 1) return fail(ctx, OFDIS_ERR_ARG, "sor_lane: 0 or 1");
+    ctx->sor_lane = value;
   } else if (!strcmp(name, "sor_fast")) {
     if (value != 0 && value != 1) return fail(ctx, OFDIS_ERR_ARG, "sor_fast: 0 or 1");
     if (!ctx->d_planes) return fail(ctx, OFDIS_ERR_ARG, "sor_fast: context created with usetvref=0");
@@ -845,6 +858,23 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
       for (size_t o = 0; o < plane; ++o)
         for (int e = 0; e < per_f; ++e) dst[o * per_f + e] = is_rec ? raw[o * 8 + e] : raw[(size_t)e * plane + o];
       return (long)(plane * per_f);
+    }
+    if (ctx->sor_lane && sor_lane_fits(L->h, 1)) {  // lane-skewed layout (VarRefPlanes, lane mode)
+      VarRefPlanes lp{};
+      lp.nb = (L->h + 31) / 32;
+      lp.ndiag = L->w + 32;
+      const int per_l = is_rec ? (L->nop == 2 ? 8 : 5) : 2;
+      const size_t stride_l = lane_frame_f4(L->w, L->h);
+      if (plane * per_l > max_floats) return OFDIS_ERR_ARG;
+      std::vector<float> raw(stride_l * 4);
+      if (cudaMemcpyAsync(raw.data(), ctx->planes.rec + (size_t)fr * stride_l, sizeof(float) * raw.size(), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return OFDIS_ERR_CUDA;
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return OFDIS_ERR_CUDA;
+      for (int j = 0; j < L->h; ++j)
+        for (int i = 0; i < L->w; ++i)
+          for (int e = 0; e < per_l; ++e)
+            dst[((size_t)j * L->pitch + i) * per_l + e] =
+                is_rec ? raw[lane_rec_f4(lp, i, j, e >> 2) * 4 + (e & 3)] : raw[lane_dudv_f2(lp, i, j) * 2 + e];
+      return (long)(plane * per_l);
     }
     VarRefPlanes bp{};
     if (!sor_band_plan(L->w, L->h, ctx->sor_rt, ctx->sor_single_max, ctx->sor_max_cluster, ctx->nop, ctx->prm.tv_solverit, &bp)) return OFDIS_ERR_UNSUPPORTED;

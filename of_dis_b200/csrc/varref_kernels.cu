@@ -21,7 +21,7 @@ namespace {
 
 #ifdef OFDIS_SOR_TIMING
 // debug build only: per-warp cycle stamps of a few super-steps of frame 0 (tools/sor_timing.py)
-__device__ long long g_sor_times[64 * 8 * 16];
+__device__ long long g_sor_times[64 * 8 * 16];  // sor_lane_kernel: [warp 16][chunk 32][4 stamps]
 #define SOR_STAMP(slot, dep1, dep2)                                                           \
   do {                                                                                        \
     if (fr == 0 && (tid & 31) == 0 && T >= 40 && T < 48) {                                    \
@@ -155,13 +155,18 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   // Records and (du,dv) of pixel (x,y).  Exact mode: the band-skewed lane rows (band_f4): chunk f of a
   // block holds field f of its 4 pixels, du is chunk nq, dv chunk nq+1.  Fast mode (red-black SOR):
   // natural layout, 8 floats per pixel, (du,dv) in the current ping-pong planes.
-  const bool fast = pl.fast != 0;
+  // Lane mode (sor_lane_kernel): lane-skewed layout, the record is two float4 (lane_rec_f4), (du,dv) one float2.
+  const bool fast = pl.fast != 0, lane = pl.lane != 0;
   float* const rec = fast ? pl.frec + (size_t)fr * pl.frec_stride : reinterpret_cast<float*>(pl.rec + (size_t)fr * pl.rec_stride);
   float* const dudv = fast ? pl.fdu + (size_t)fr * pl.fdu_stride + (size_t)pl.fcur * 2 * pl.plane : rec;
   const int fs = fast ? 1 : 4;                       // floats between consecutive record fields of a pixel
-  const int dv_off = fast ? (int)pl.plane : 4;       // from du to dv
-  auto rec_idx = [&pl, fast, pitch](int x, int y) { return fast ? (y * pitch + x) * 8 : (int)band_f4(pl, x >> 2, y, 0) * 4 + (x & 3); };
-  auto du_idx = [&pl, fast, pitch](int x, int y) { return fast ? y * pitch + x : (int)band_f4(pl, x >> 2, y, pl.nq) * 4 + (x & 3); };
+  const int dv_off = lane ? 1 : (fast ? (int)pl.plane : 4);  // from du to dv
+  auto rec_idx = [&pl, fast, lane, pitch](int x, int y) {
+    return lane ? (int)lane_rec_f4(pl, x, y, 0) * 4 : (fast ? (y * pitch + x) * 8 : (int)band_f4(pl, x >> 2, y, 0) * 4 + (x & 3));
+  };
+  auto du_idx = [&pl, fast, lane, pitch](int x, int y) {
+    return lane ? (int)lane_dudv_f2(pl, x, y) * 2 : (fast ? y * pitch + x : (int)band_f4(pl, x >> 2, y, pl.nq) * 4 + (x & 3));
+  };
 
   // uu = wx + du (vv likewise); first iteration: uu = wx (refine_variational.cpp:189-190).
   // Coordinates are clamped, which also realises the replicate border of the 3-tap
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   if (first) {
     dudv[bd] = 0.0f;
     dudv[bd + dv_off] = 0.0f;
-    if (!fast && i == w - 1)
+    if (!fast && !lane && i == w - 1)
       for (int t = (i & 3) + 1; t < 4; ++t) dudv[bd + t - (i & 3)] = dudv[bd + 4 + t - (i & 3)] = 0.0f;
   } else {
     u = dudv[bd];
@@ -365,6 +370,11 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     const float det = iA11 * iA22 - A12 * A12;
     // record of the 4-pixel block, SoA: float4 f of the block holds field f of its 4 pixels;
     // fields: a11^-1, a12^-1, a22^-1, b1, b2, sh, sv, sv(row above)
+    if (lane) {
+      float4* const r4 = reinterpret_cast<float4*>(rec + b0);
+      r4[0] = make_float4(iA11 / det, A12 / -det, iA22 / det, B1);
+      r4[32] = make_float4(B2, hh, vv, vt);
+    } else {
     rec[b0] = iA11 / det;
     rec[b0 + fs] = A12 / -det;
     rec[b0 + 2 * fs] = iA22 / det;
@@ -373,6 +383,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     rec[b0 + 5 * fs] = hh;
     rec[b0 + 6 * fs] = vv;
     rec[b0 + 7 * fs] = vt;
+    }
   } else {
     // sor_coupled_slow_but_readable_DE (solver.c:438-460): A11 = a11 + sum_dpsis (top,left,bottom,right)
     float sum = 0.0f;
@@ -381,11 +392,17 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     if (j < h - 1) sum += vv;
     if (i < w - 1) sum += hh;
     // stereo record fields: A11 = a11 + sum, b1, sh, sv, sv(row above)
+    if (lane) {
+      float4* const r4 = reinterpret_cast<float4*>(rec + b0);
+      r4[0] = make_float4(A11 + sum, B1, hh, vv);
+      r4[32] = make_float4(vt, 0.f, 0.f, 0.f);
+    } else {
     rec[b0] = A11 + sum;
     rec[b0 + fs] = B1;
     rec[b0 + 2 * fs] = hh;
     rec[b0 + 3 * fs] = vv;
     rec[b0 + 4 * fs] = vt;
+    }
   }
   }  // rows of this thread
 }
@@ -423,6 +440,7 @@ __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
 }
 
 #include "sor_wave_kernel.cuh"
+#include "sor_lane_kernel.cuh"
 #include "sor_redblack_kernel.cuh"
 
 // K12 at the end of the level: flow = w + dw (refine_variational.cpp:210-221; stereo clamp
@@ -433,11 +451,11 @@ __global__ void __launch_bounds__(256) flow_update_kernel(LevelGeom g, VarRefPla
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
   const int fr = blockIdx.z, frame = frame_of(g, f0, fr);
   if (i >= g.w || j >= g.h) return;
-  const bool fast = pl.fast != 0;
+  const bool fast = pl.fast != 0, lane = pl.lane != 0;
   const float* dudv = fast ? pl.fdu + (size_t)fr * pl.fdu_stride + (size_t)pl.fcur * 2 * pl.plane
                            : reinterpret_cast<const float*>(pl.rec + (size_t)fr * pl.rec_stride);
-  const size_t b = fast ? (size_t)j * g.pitch + i : band_f4(pl, i >> 2, j, pl.nq) * 4 + (i & 3);
-  const size_t dv_off = fast ? pl.plane : 4;
+  const size_t b = lane ? lane_dudv_f2(pl, i, j) * 2 : (fast ? (size_t)j * g.pitch + i : band_f4(pl, i >> 2, j, pl.nq) * 4 + (i & 3));
+  const size_t dv_off = lane ? 1 : (fast ? pl.plane : 4);
   float* f = g.flow + (size_t)frame * g.flow_frame_stride + ((size_t)j * g.w + i) * NOP;
   if (NOP == 2) {
     const float2 wv = *reinterpret_cast<const float2*>(f);
@@ -564,6 +582,25 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl_in, const 
       ++launches;
       continue;
     }
+    if (pl.lane) {  // pixel wavefront, warps synchronised through shared-memory flags (levels of few 32-row bands)
+      const int kll = sl_sweeps_per_launch(pl.nb, K);
+      if (kll < 1) return -1;
+      for (int s = 0; s < K; s += kll) {
+        ProfScope scope(prof, KC_VR_SOR);
+        const int kk = (K - s < kll) ? K - s : kll;
+        const size_t smem = sl_smem_bytes(pl.nb, kk);
+        static size_t smem_set[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && smem_set[dev] < smem) {
+          if (cudaFuncSetAttribute(sor_lane_kernel<NOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+          smem_set[dev] = smem;
+        }
+        sor_lane_kernel<NOP><<<nf, pl.nb * kk * 32, smem, st>>>(g, pl, vp, kk);
+        ++launches;
+      }
+      continue;
+    }
     for (int s = 0; s < K; s += kl) {
       ProfScope scope(prof, KC_VR_SOR);
       if (launch_sor<NOP>(g, pl, vp, nf, (K - s < kl) ? K - s : kl, st) != cudaSuccess) return -1;
@@ -583,6 +620,8 @@ extern "C" int ofdis_debug_sor_times(long long* dst) {
   return cudaMemcpyFromSymbol(dst, g_sor_times, sizeof(g_sor_times)) == cudaSuccess ? 0 : -1;
 }
 #endif
+
+bool sor_lane_fits(int h, int K) { return sl_sweeps_per_launch((h + 31) / 32, K) >= 1; }
 
 bool rb_smem_limit_exceeded(int nop, int K) { return K < 1 || rb_smem_bytes(nop, K) > 227 * 1024; }
 

@@ -281,6 +281,7 @@ def test_cluster_sor_on_small_levels_vs_oracle(name, single_max, rt, api, oracle
         i0, i1, _ = synth.synthetic_pair(h, w, ch, seed=1 + s, amp=amp, stereo=stereo)
         pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
     ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, 2)
+    ctx.set_option("sor_lane", 0)  # this test is about the block wavefront (sor_wave_kernel)
     ctx.set_option("sor_single_max", single_max)
     ctx.set_option("sor_rows_per_thread", rt)
     for f, p in enumerate(pyrs):
@@ -314,10 +315,56 @@ def test_sor_tile_heights_vs_oracle(name, rt, api, oracle_port):
     i0, i1, _ = synth.synthetic_pair(h, w, ch, seed=3, amp=amp, stereo=stereo)
     pyr = preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s)
     ctx = api.Context(prm, pyr.width, pyr.height, pyr.imgpadding, 1)
+    ctx.set_option("sor_lane", 0)
     ctx.set_option("sor_rows_per_thread", rt)
     ctx.upload_pyramids(0, pyr)
     ctx.run(1)
     assert_bits(ctx.get_flow(0, prm.sc_l), oracle_port.port_run(pyr, prm), "run rt=%d" % rt)
+    ctx.close()
+
+
+LANE_CASES = ["cfg2_1024x436_gray_op2", "cfg1_640x480_gray_op2", "rgb_op3_l1cost_small", "stereo_op4_small",
+              "gray_p6_nopatnorm_sor5", "gray_sor2_rows70", "stereo_sor1_rows100"]
+
+
+@pytest.mark.parametrize("lane", [1, 0])
+@pytest.mark.parametrize("name", LANE_CASES)
+def test_lane_sor_and_block_sor_vs_oracle(name, lane, api, oracle_port):
+    """ofdis_set_option("sor_lane"): the pixel wavefront (sor_lane_kernel: warps synchronised through shared-memory
+    flags; 1..5 bands of 32 rows, partial last bands, 1..5 sweeps -- more than fit one launch included --, flow and
+    stereo) and the block wavefront (sor_wave_kernel) give the reference's bits: (du,dv) after two inner
+    iterations and the whole run, three frames per launch, graph replay."""
+    h, w, ch, mk, amp, stereo = CASES[name]
+    prm = mk()
+    pyrs = []
+    for s in range(3):
+        i0, i1, _ = synth.synthetic_pair(h, w, ch, seed=11 + s, amp=amp, stereo=stereo)
+        pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
+    ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, 3)
+    ctx.set_option("sor_lane", lane)
+    for f, p in enumerate(pyrs):
+        ctx.upload_pyramids(f, p)
+    lv = prm.sc_l
+    hh, ww = pyrs[0].level_shape(lv)
+    rng = np.random.default_rng(5)
+    dense = (rng.standard_normal((hh, ww, prm.nop)) * 1.5).astype(np.float32)
+    if stereo:
+        dense = -np.abs(dense)
+    st = oracle_port.varref_stages(pyrs[2], prm, lv, dense, n_iters=2)
+    ctx.set_flow(2, lv, dense)
+    ctx.varref_refine(lv, 0, 3, n_inner=2)
+    rec = ctx.debug_get("rec", 2, lv)
+    it = st["iters"][1]
+    assert_bits(rec[..., 1 if prm.nop == 1 else 3], it["b1"], "rec.b1")
+    dudv = ctx.debug_get("dudv", 2, lv)
+    assert_bits(dudv[..., 0], it["du"], "du")
+    if prm.nop == 2:
+        assert_bits(dudv[..., 1], it["dv"], "dv")
+    ctx.set_graph_mode(True)
+    for _ in range(2):
+        ctx.run(3)
+    for f, p in enumerate(pyrs):
+        assert_bits(ctx.get_flow(f, prm.sc_l), oracle_port.port_run(p, prm), "run, frame %d" % f)
     ctx.close()
 
 
