@@ -657,7 +657,7 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   if (ctx->sor_lane && !pl.fast && sor_lane_fits(L->h, 1)) {  // lane-skewed layout, bands of 32 rows
     pl.lane = 1;
     pl.nb = (L->h + 31) / 32;
-    pl.ndiag = L->w + 32;
+    pl.ndiag = lane_ndiag(L->w);
     pl.rec_stride = lane_frame_f4(L->w, L->h);
   }
   pl.frec_stride = pl.plane * 8;   // fast mode: natural layout at this level's plane size
@@ -862,7 +862,7 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
     if (ctx->sor_lane && sor_lane_fits(L->h, 1)) {  // lane-skewed layout (VarRefPlanes, lane mode)
       VarRefPlanes lp{};
       lp.nb = (L->h + 31) / 32;
-      lp.ndiag = L->w + 32;
+      lp.ndiag = lane_ndiag(L->w);
       const int per_l = is_rec ? (L->nop == 2 ? 8 : 5) : 2;
       const size_t stride_l = lane_frame_f4(L->w, L->h);
       if (plane * per_l > max_floats) return OFDIS_ERR_ARG;
@@ -873,7 +873,7 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
         for (int i = 0; i < L->w; ++i)
           for (int e = 0; e < per_l; ++e)
             dst[((size_t)j * L->pitch + i) * per_l + e] =
-                is_rec ? raw[lane_rec_f4(lp, i, j, e >> 2) * 4 + (e & 3)] : raw[lane_dudv_f2(lp, i, j) * 2 + e];
+                is_rec ? raw[lane_rec_f4(lp, i, j, e >> 2) * 4 + (e & 3)] : raw[lane_dudv_f(lp, i, j) + e];
       return (long)(plane * per_l);
     }
     VarRefPlanes bp{};

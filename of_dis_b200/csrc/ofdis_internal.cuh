@@ -75,9 +75,10 @@ struct VarRefPlanes {
   // "Fast" refinement (ofdis_set_option "sor_fast"; NOT bit-exact): red-black
   // SOR on natural-layout arrays -- records [frames][h][pitch][8] (a11^-1 a12^-1 a22^-1 b1 b2 sh sv -; stereo
   // A11 b1 sh sv), (du,dv) as two ping-pong buffers of two planes each [frames][2][2][h*pitch].
-  // Lane mode (sor_lane_kernel.cuh; exact, levels of few 32-row bands): nb = bands of 32 rows, ndiag = w + 32,
-  // records [frames][nb][t = x + (y & 31)][half][lane = y & 31] float4 (flow: a11^-1 a12^-1 a22^-1 b1 | b2 sh sv
-  // sv_top; stereo: A11 b1 sh sv | sv_top - - -), then (du,dv) [frames][nb][t][lane] float2 behind them.
+  // Lane mode (sor_lane_kernel.cuh; exact, levels of few 32-row bands): nb = bands of 32 rows, ndiag = lane_ndiag(w),
+  // records [frames][nb][t = x/2 + (y & 31)][q = 2 (x & 1) + half][lane = y & 31] float4 (flow: a11^-1 a12^-1 a22^-1
+  // b1 | b2 sh sv sv_top; stereo: A11 b1 sh sv | sv_top - - -), then (du,dv) of the two pixels of a block as one
+  // float4 [frames][nb][t][lane] behind them.
   int lane;                // 1 = lane-skewed layout + sor_lane_kernel for this level
   int fast;                // 0 = exact lexicographic SOR (default)
   int fcur;                // ping-pong buffer that holds the current (du,dv)
@@ -94,17 +95,19 @@ __host__ __device__ __forceinline__ size_t band_f4(const VarRefPlanes& pl, int I
   return ((size_t)((j >> pl.hbshift) * pl.ndiag + I + rl) * pl.hpad + rl) * pl.lpitch + s * (pl.nq + 2) + q;
 }
 
-// lane mode: float4 index of record half `half` (0, 1) and float2 index of (du,dv) of pixel (x, y), relative to
-// the frame's pl.rec; float4 per frame
+// lane mode: rows in bands of 32 (lane = y & 31), columns in blocks of two; block I of lane l sits at t = I + l.
+// float4 index of record half `half` (0, 1) and FLOAT index of du (dv = +1) of pixel (x, y), relative to the
+// frame's pl.rec; entries per band; float4 per frame
+__host__ __device__ __forceinline__ int lane_ndiag(int w) { return ((w + 1) >> 1) + 48; }
 __host__ __device__ __forceinline__ size_t lane_rec_f4(const VarRefPlanes& pl, int x, int y, int half) {
   const int l = y & 31;
-  return ((size_t)((y >> 5) * pl.ndiag + x + l) * 2 + half) * 32 + l;
+  return ((size_t)((y >> 5) * pl.ndiag + (x >> 1) + l) * 4 + 2 * (x & 1) + half) * 32 + l;
 }
-__host__ __device__ __forceinline__ size_t lane_dudv_f2(const VarRefPlanes& pl, int x, int y) {
+__host__ __device__ __forceinline__ size_t lane_dudv_f(const VarRefPlanes& pl, int x, int y) {
   const int l = y & 31;
-  return (size_t)pl.nb * pl.ndiag * 128 + (size_t)((y >> 5) * pl.ndiag + x + l) * 32 + l;
+  return ((size_t)pl.nb * pl.ndiag * 128 + (size_t)((y >> 5) * pl.ndiag + (x >> 1) + l) * 32 + l) * 4 + 2 * (x & 1);
 }
-__host__ __device__ __forceinline__ size_t lane_frame_f4(int w, int h) { return (size_t)((h + 31) / 32) * (w + 32) * 80; }
+__host__ __device__ __forceinline__ size_t lane_frame_f4(int w, int h) { return (size_t)((h + 31) / 32) * lane_ndiag(w) * 160; }
 
 // Band plan of a level for the SOR (sor_wave_kernel.cuh).  `rt` rows per lane (tiles of 4 columns x
 // rt rows per thread and super-step: the wavefront needs W/4 + h/rt super-steps).  Levels of up to

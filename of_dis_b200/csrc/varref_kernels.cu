@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
     return lane ? (int)lane_rec_f4(pl, x, y, 0) * 4 : (fast ? (y * pitch + x) * 8 : (int)band_f4(pl, x >> 2, y, 0) * 4 + (x & 3));
   };
   auto du_idx = [&pl, fast, lane, pitch](int x, int y) {
-    return lane ? (int)lane_dudv_f2(pl, x, y) * 2 : (fast ? y * pitch + x : (int)band_f4(pl, x >> 2, y, pl.nq) * 4 + (x & 3));
+    return lane ? (int)lane_dudv_f(pl, x, y) : (fast ? y * pitch + x : (int)band_f4(pl, x >> 2, y, pl.nq) * 4 + (x & 3));
   };
 
   // uu = wx + du (vv likewise); first iteration: uu = wx (refine_variational.cpp:189-190).
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(256) flow_update_kernel(LevelGeom g, VarRefPla
   const bool fast = pl.fast != 0, lane = pl.lane != 0;
   const float* dudv = fast ? pl.fdu + (size_t)fr * pl.fdu_stride + (size_t)pl.fcur * 2 * pl.plane
                            : reinterpret_cast<const float*>(pl.rec + (size_t)fr * pl.rec_stride);
-  const size_t b = lane ? lane_dudv_f2(pl, i, j) * 2 : (fast ? (size_t)j * g.pitch + i : band_f4(pl, i >> 2, j, pl.nq) * 4 + (i & 3));
+  const size_t b = lane ? lane_dudv_f(pl, i, j) : (fast ? (size_t)j * g.pitch + i : band_f4(pl, i >> 2, j, pl.nq) * 4 + (i & 3));
   const size_t dv_off = lane ? 1 : (fast ? pl.plane : 4);
   float* f = g.flow + (size_t)frame * g.flow_frame_stride + ((size_t)j * g.w + i) * NOP;
   if (NOP == 2) {

@@ -16,9 +16,9 @@ def build():
     from of_dis_b200 import build as B
     os.makedirs(EXP, exist_ok=True)
     procs = []
-    for v in list(VARIANTS) + ["t"]:
+    for v in ONLY or (list(VARIANTS) + ["t"]):
         out = os.path.join(EXP, "libofdis_lane%s.so" % v)
-        defs = ["-DOFDIS_SOR_TIMING"] if v == "t" else ["-DOFDIS_EXP_LANE=%d" % v]
+        defs = ["-DOFDIS_SOR_TIMING"] if v == "t" else (["-DOFDIS_EXP_UNROLL=%s" % v[1:]] if str(v).startswith("u") else ["-DOFDIS_EXP_LANE=%s" % v])
         cmd = [B._nvcc()] + B.NVCC_FLAGS + defs + [os.path.join(B.CSRC, s) for s in B.SOURCES] + ["-ldl", "-o", out]
         procs.append((v, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for v, p in procs:
@@ -62,15 +62,17 @@ def child(timeline):
     print(json.dumps(out))
 
 
+ONLY = [a for a in sys.argv[1:] if not a.startswith("--")]  # e.g. 0 5 u1 u2 u4 (uN: product with the step loop unrolled N times)
+
 if __name__ == "__main__":
     if "--build" in sys.argv:
         build()
     elif "--child" in sys.argv:
         child("--timeline" in sys.argv)
     else:
-        for v in list(VARIANTS) + ["t"]:
+        for v in ONLY or (list(VARIANTS) + ["t"]):
             lib = os.path.join(EXP, "libofdis_lane%s.so" % v)
             env = dict(os.environ, OFDIS_LIB=lib)
             args = [sys.executable, os.path.abspath(__file__), "--child"] + (["--timeline"] if v == "t" else [])
             r = subprocess.run(args, env=env, capture_output=True, text=True, timeout=600)
-            print(json.dumps({"variant": v, "what": VARIANTS.get(v, "product + cycle stamps")}), r.stdout.strip().splitlines()[-1] if r.returncode == 0 and r.stdout.strip() else ("FAILED " + r.stderr[-600:]), flush=True)
+            print(json.dumps({"variant": v, "what": VARIANTS.get(v if not str(v).isdigit() else int(v), "product + cycle stamps" if v == "t" else "unroll")}), r.stdout.strip().splitlines()[-1] if r.returncode == 0 and r.stdout.strip() else ("FAILED " + r.stderr[-600:]), flush=True)

@@ -19,7 +19,7 @@ import sys
 
 import numpy as np
 
-C, R, D, DS, DP = 8, 32, 6, 8, 8
+C, P, R, D, DS, DP = 8, 4, 32, 6, 8, 8
 f32 = np.float32
 
 
@@ -54,19 +54,20 @@ class Model:
         self.w, self.h, self.K, self.rng, self.land_late = w, h, K, rng, land_late
         self.nb = (h + 31) // 32
         self.nw = self.nb * K
-        self.ND = w + 32
-        self.TLp = (w + 31 + C - 1) // C * C
+        self.W2 = (w + 1) // 2
+        self.ND = self.W2 + 48
+        self.TLp = (self.W2 + min(h, 32) - 1 + C - 1) // C * C
         nb, ND = self.nb, self.ND
-        # global memory, lane-skewed (VarRefPlanes lane mode)
-        self.rec_g = np.full((nb, ND, 32, 8), np.nan, f32)
-        self.dudv_g = np.full((nb, ND, 32, 2), np.nan, f32)
-        # shared memory; *_id arrays hold the entry number stored last (-1: never written)
+        # global memory, lane-skewed (VarRefPlanes lane mode): per (band, t, lane) two pixels
+        self.rec_g = np.full((nb, ND, 32, 2, 8), np.nan, f32)
+        self.dudv_g = np.full((nb, ND, 32, 4), np.nan, f32)
+        # shared memory; *_id arrays hold the entry number stored last
         self.prog = np.zeros(32, np.int64)
-        self.ring = np.full((self.nw, R, 32, 2), np.nan, f32)
+        self.ring = np.full((self.nw, R, 32, 4), np.nan, f32)
         self.ring_id = np.full((self.nw, R), -10**9, np.int64)
-        self.recs = np.full((self.nw, DS, 32, 8), np.nan, f32)
-        self.recs_id = np.full((self.nw, DS, 32), -10**9, np.int64)
-        self.prev = np.full((nb, DP, 33, 2), np.nan, f32)
+        self.recs = np.full((self.nw, DS, 32, 2, 8), np.nan, f32)
+        self.recs_id = np.full((self.nw, DS), -10**9, np.int64)
+        self.prev = np.full((nb, DP, 33, 4), np.nan, f32)
         self.prev_id = np.full((nb, DP, 33), -10**9, np.int64)
         self.reads_checked = 0
 
@@ -74,8 +75,8 @@ class Model:
         for j in range(self.h):
             b, l = divmod(j, 32)
             for i in range(self.w):
-                self.rec_g[b, i + l, l] = rec[j, i]
-                self.dudv_g[b, i + l, l] = (du[j, i], dv[j, i])
+                self.rec_g[b, i // 2 + l, l, i & 1] = rec[j, i]
+                self.dudv_g[b, i // 2 + l, l, 2 * (i & 1):2 * (i & 1) + 2] = (du[j, i], dv[j, i])
 
     def result(self):
         du = np.zeros((self.h, self.w), f32)
@@ -83,18 +84,17 @@ class Model:
         for j in range(self.h):
             b, l = divmod(j, 32)
             for i in range(self.w):
-                du[j, i], dv[j, i] = self.dudv_g[b, i + l, l]
+                du[j, i], dv[j, i] = self.dudv_g[b, i // 2 + l, l, 2 * (i & 1):2 * (i & 1) + 2]
         return du, dv
 
     def warp(self, wi, omega):
         """Generator: one warp of the kernel; yields at every point where another warp may run."""
-        nb, K, w, h, ND, TLp = self.nb, self.K, self.w, self.h, self.ND, self.TLp
+        nb, K, w, h, ND, TLp, W2 = self.nb, self.K, self.w, self.h, self.ND, self.TLp, self.W2
         k, b = divmod(wi, nb)
         lanes = np.arange(32)
         j = 32 * b + lanes
         row_ok = j < h
         first_row, last_row = j == 0, j >= h - 1
-        w_eff = np.where(row_ok, w, 0)
         has_above, has_below = b > 0, b + 1 < nb
         k0, klast = k == 0, k == K - 1
         om = f32(omega)
@@ -106,33 +106,28 @@ class Model:
                 x = kk * nb + bb
                 off[x] = max(off[x], o)
 
-        dep(b, k - 1, C + 1)
-        dep(b + 1, k - 1, C - 31)
-        dep(b - 1, k, C + 31)
-        dep(b, k + 1, C - 1 - R)
-        dep(b - 1, k + 1, C - 1 - R + 32)
-        dep(b + 1, k, C - 1 - R - 30)
+        dep(b, k - 1, 3)
+        dep(b + 1, k - 1, -29)
+        dep(b - 1, k, 33)
+        dep(b, k + 1, -R + 1)
+        dep(b - 1, k + 1, -R + 32)
+        dep(b + 1, k, -R - 30)
 
         pending = []  # cp.async groups: lists of closures
 
         def issue(tp, grp):
-            ok = row_ok & (tp - lanes >= 0) & (tp - lanes < w_eff)
-            if ok.any():
-                def land(ok=ok, tp=tp):  # global memory is read when the copy lands (latest) or at issue (earliest)
-                    src = self.rec_g[b, tp]
-                    self.recs[wi, tp % DS][ok] = src[ok]
-                    self.recs_id[wi, tp % DS][ok] = tp
-                grp.append(land)
+            def land(tp=tp):  # global memory is read when the copy lands (latest) or at issue (earliest)
+                self.recs[wi, tp % DS] = self.rec_g[b, tp]
+                self.recs_id[wi, tp % DS] = tp
+            grp.append(land)
             if k0:
                 te = tp + 1
-                ok2 = row_ok & (te - lanes >= 0) & (te - lanes < w_eff)
-                if ok2.any():
-                    def land2(ok2=ok2, te=te):
-                        src2 = self.dudv_g[b, te]
-                        self.prev[b, te % DP][:32][ok2] = src2[ok2]
-                        self.prev_id[b, te % DP][:32][ok2] = te
-                    grp.append(land2)
-                if has_below and 0 <= te - 32 < w:
+
+                def land2(te=te):
+                    self.prev[b, te % DP][:32] = self.dudv_g[b, te]
+                    self.prev_id[b, te % DP][:32] = te
+                grp.append(land2)
+                if has_below and te >= 32:
                     def land3(te=te):
                         self.prev[b, te % DP][32] = self.dudv_g[b + 1, te - 32, 0]
                         self.prev_id[b, te % DP][32] = te
@@ -152,112 +147,138 @@ class Model:
                     f()
 
         g0 = []
-        if k0 and row_ok[0]:
+        if k0:
             def land0():
-                self.prev[b, 0][0] = self.dudv_g[b, 0, 0]
-                self.prev_id[b, 0][0] = 0
+                self.prev[b, 0][:32] = self.dudv_g[b, 0]
+                self.prev_id[b, 0][:32] = 0
             g0.append(land0)
         for tp in range(D):
             grp = g0 if tp == 0 else []
             issue(tp, grp)
             commit(grp)
 
-        du_l = np.zeros(32, f32)
-        dv_l = np.zeros(32, f32)
-        hl = np.zeros(32, f32)
-        nxt = np.zeros((32, 2), f32)
-        pr = (k - 1) * nb + b if k > 0 else 0
-        for t0 in range(0, TLp, C):
-            if t0 > 0:
-                self.prog[wi] = t0
-            need = np.where(off == NONE, 0, np.clip(t0 + off, 0, TLp))
+        watched = off != NONE
+
+        def blocked(t):
+            lim = np.where(self.prog >= TLp, 1 << 40, self.prog - off)[watched]
+            return lim.size > 0 and t > lim.min()
+
+        def ensure(t):
             spins = 0
-            while not (self.prog >= need).all():
+            while blocked(t):
                 spins += 1
                 if spins > 200000:
-                    raise RuntimeError("deadlock: warp %d (b=%d,k=%d) at t0=%d need=%s prog=%s" % (wi, b, k, t0, need[:self.nw], self.prog[:self.nw]))
+                    raise RuntimeError("deadlock: warp %d (b=%d,k=%d) at t=%d prog=%s" % (wi, b, k, t, self.prog[:self.nw]))
                 yield
-            if t0 == 0:
-                if k0:
-                    wait(D - 1)
-                    nxt = self.prev[b, 0][:32].copy()
-                    assert self.prev_id[b, 0][0] == 0 or not row_ok[0]
+
+        pr = (k - 1) * nb + b if k > 0 else 0
+
+        def load_operands(t1):
+            """operands of step t1 (records, next/bottom previous-sweep blocks, halo row), with id checks"""
+            I1 = t1 - lanes
+            act1 = row_ok & (I1 >= 0) & (I1 < W2)
+            has_r1 = 2 * I1 + 2 < w  # the block's second pixel has a right neighbour in the next block
+            rec = self.recs[wi, t1 % DS].copy()
+            if act1.any():
+                assert self.recs_id[wi, t1 % DS] == t1, "record ring: stale slot"
+            if k0:
+                slot = (t1 + 1) % DP
+                nx = self.prev[b, slot][:32].copy()
+                bt = self.prev[b, slot][1:33].copy()
+                assert (self.prev_id[b, slot][:32][act1 & has_r1] == t1 + 1).all(), "prev ring: next block stale"
+                assert (self.prev_id[b, slot][1:33][act1 & ~last_row] == t1 + 1).all(), "prev ring: bottom block stale"
+            else:
+                slot = (t1 + 1) % R
+                nx = self.ring[pr, slot].copy()
+                if (act1 & (has_r1 | ~last_row))[:31].any() or (act1 & has_r1)[31]:
+                    assert self.ring_id[pr, slot] == t1 + 1, "ring (b,k-1): entry t+1 stale (%d)" % self.ring_id[pr, slot]
+                bt = np.empty((32, 4), f32)
+                bt[:31] = nx[1:]
+                if has_below:
+                    bt[31] = self.ring[pr + 1, slot, 0]
+                    if act1[31] and not last_row[31]:
+                        assert self.ring_id[pr + 1, slot] == t1 - 31, "ring (b+1,k-1): entry t-31 stale"
                 else:
-                    nxt = self.ring[pr, 0].copy()
-                    assert self.ring_id[pr, 0] == 0
+                    bt[31] = nx[31]
+            th = np.zeros(4, f32)
+            if has_above:
+                slot_t = (t1 + 31) % R
+                th = self.ring[wi - 1, slot_t, 31].copy()
+                if act1[0]:
+                    assert self.ring_id[wi - 1, slot_t] == t1 + 31, "ring (b-1,k): entry t+31 stale"
+            return rec, nx, bt, th
+
+        def pixel(r8, ou, ov, ru, rv, tu, tv, bu, bv, lu, lv, hl, has_l, has_r):
+            with np.errstate(all="ignore"):
+                a11, a12, a22, b1, b2, hh, vv, vt = (r8[:, q] for q in range(8))
+                du_r = np.where(has_r, ru, f32(0))
+                dv_r = np.where(has_r, rv, f32(0))
+                t1u, t1v = hh * du_r, hh * dv_r
+                t2u, t2v = t1u + vt * tu, t1v + vt * tv
+                bsu, bsv = np.where(first_row, t1u, t2u), np.where(first_row, t1v, t2v)
+                t3u, t3v = bsu + vv * bu, bsv + vv * bv
+                s1 = np.where(last_row, bsu, t3u) + b1
+                s2 = np.where(last_row, bsv, t3v) + b2
+                B1w, B2w = hl * lu + s1, hl * lv + s2
+                B1, B2 = np.where(has_l, B1w, s1), np.where(has_l, B2w, s2)
+                du = ou + om * (a11 * B1 + a12 * B2 - ou)
+                dv = ov + om * (a12 * B1 + a22 * B2 - ov)
+            return du.astype(f32), dv.astype(f32)
+
+        yield from ensure(-1)
+        wait(D - 2)
+        if k0:
+            cur = self.prev[b, 0][:32].copy()
+            assert self.prev_id[b, 0][0] == 0
+        else:
+            cur = self.ring[pr, 0].copy()
+            assert self.ring_id[pr, 0] == 0
+        rec, nxt, bot, th = load_operands(0)
+        res = np.zeros((32, 4), f32)
+        hl = np.zeros(32, f32)
+        for t0 in range(0, TLp, C):
             for s in range(C):
                 t = t0 + s
-                i = t - lanes
+                if s % P == 0 and t > 0:
+                    self.prog[wi] = t
+                I = t - lanes
+                if s % 2 == 0:
+                    yield from ensure(t + 1)  # this step and the next
+                top = np.vstack((res[:1], res[:31]))
                 grp = []
                 issue(t + D, grp)
                 commit(grp)
-                wait(D)
+                wait(D - 1)
                 yield
-                act = row_ok & (i >= 0) & (i < w)
-                # records
-                rec = self.recs[wi, t % DS].copy()
-                assert (self.recs_id[wi, t % DS][act] == t).all(), "record ring: stale slot"
-                own = nxt
-                has_l, has_r = i > 0, i + 1 < w
-                if k0:
-                    slot = (t + 1) % DP
-                    nxt = self.prev[b, slot][:32].copy()
-                    bot = self.prev[b, slot][1:33].copy()
-                    chk = act & has_r
-                    assert (self.prev_id[b, slot][:32][chk] == t + 1).all(), "prev ring: right neighbour stale"
-                    chk = act & ~last_row
-                    assert (self.prev_id[b, slot][1:33][chk] == t + 1).all(), "prev ring: bottom neighbour stale"
-                else:
-                    slot = (t + 1) % R
-                    nxt = self.ring[pr, slot].copy()
-                    if (act & (has_r | ~last_row))[:31].any() or (act & has_r)[31]:
-                        assert self.ring_id[pr, slot] == t + 1, "ring (b,k-1): entry t+1 stale (%d)" % self.ring_id[pr, slot]
-                    bot = np.empty((32, 2), f32)
-                    bot[:31] = nxt[1:]
-                    if has_below:
-                        bot[31] = self.ring[pr + 1, slot, 0]
-                        if act[31] and not last_row[31]:
-                            assert self.ring_id[pr + 1, slot] == t - 31, "ring (b+1,k-1): entry t-31 stale"
-                    else:
-                        bot[31] = nxt[31]
-                self.reads_checked += int(act.sum())
-                top_u = np.concatenate(([du_l[0]], du_l[:31]))
-                top_v = np.concatenate(([dv_l[0]], dv_l[:31]))
-                if has_above and t < w:
-                    slot_t = (t + 31) % R
-                    top_u[0], top_v[0] = self.ring[wi - 1, slot_t, 31]
-                    if act[0]:
-                        assert self.ring_id[wi - 1, slot_t] == t + 31, "ring (b-1,k): entry t+31 stale"
-                with np.errstate(all="ignore"):
-                    a11, a12, a22, b1, b2, hh, vv, vt = (rec[:, q] for q in range(8))
-                    du_r = np.where(has_r, nxt[:, 0], f32(0))
-                    dv_r = np.where(has_r, nxt[:, 1], f32(0))
-                    t1u, t1v = hh * du_r, hh * dv_r
-                    t2u, t2v = t1u + vt * top_u, t1v + vt * top_v
-                    bsu, bsv = np.where(first_row, t1u, t2u), np.where(first_row, t1v, t2v)
-                    t3u, t3v = bsu + vv * bot[:, 0], bsv + vv * bot[:, 1]
-                    s1 = np.where(last_row, bsu, t3u) + b1
-                    s2 = np.where(last_row, bsv, t3v) + b2
-                    B1w, B2w = hl * du_l + s1, hl * dv_l + s2
-                    B1, B2 = np.where(has_l, B1w, s1), np.where(has_l, B2w, s2)
-                    du = own[:, 0] + om * (a11 * B1 + a12 * B2 - own[:, 0])
-                    dv = own[:, 1] + om * (a12 * B1 + a22 * B2 - own[:, 1])
-                hl = hh.copy()
-                du_l, dv_l = du.astype(f32), dv.astype(f32)
-                self.ring[wi, t % R, :, 0] = du_l
-                self.ring[wi, t % R, :, 1] = dv_l
+                rec1, nxt1, bot1, th1 = load_operands(t + 1)
+                act = row_ok & (I >= 0) & (I < W2)
+                self.reads_checked += int(act.sum()) + int((act & (2 * I + 1 < w)).sum())
+                if has_above:
+                    top[0] = th
+                i0 = 2 * I
+                du0, dv0 = pixel(rec[:, 0], cur[:, 0], cur[:, 1], cur[:, 2], cur[:, 3], top[:, 0], top[:, 1], bot[:, 0], bot[:, 1],
+                                 res[:, 2], res[:, 3], hl, I > 0, i0 + 1 < w)
+                du1, dv1 = pixel(rec[:, 1], cur[:, 2], cur[:, 3], nxt[:, 0], nxt[:, 1], top[:, 2], top[:, 3], bot[:, 2], bot[:, 3],
+                                 du0, dv0, rec[:, 0, 5], np.ones(32, bool), i0 + 2 < w)
+                hl = rec[:, 1, 5].copy()
+                res = np.stack((du0, dv0, du1, dv1), axis=1)
+                yield  # the loads above are long done when the store is issued: let other warps run in between
+                self.ring[wi, t % R] = res
                 self.ring_id[wi, t % R] = t
                 if klast:
-                    for l in np.nonzero(act)[0]:
-                        self.dudv_g[b, t, l] = (du_l[l], dv_l[l])
+                    self.dudv_g[b, t] = res  # unpredicated: lanes without a block write positions nobody reads
+                rec, cur, nxt, bot, th = rec1, nxt, nxt1, bot1, th1
         self.prog[wi] = TLp
 
     def run(self, omega):
         gens = [self.warp(wi, omega) for wi in range(self.nw)]
         alive = list(range(self.nw))
+        # random interleaving with bursts: a warp runs 1..12 scheduling points in a row; some warps are starved
+        # (picked 30x less often) so that producers run far ahead of consumers and the other way round
+        weight = np.where(self.rng.random(self.nw) < 0.3, 1.0 / 30, 1.0)
         while alive:
-            # random interleaving with bursts: a warp runs 1..12 scheduling points in a row
-            wi = alive[self.rng.integers(len(alive))]
+            pw = weight[alive] / weight[alive].sum()
+            wi = alive[self.rng.choice(len(alive), p=pw)]
             for _ in range(int(self.rng.integers(1, 13))):
                 try:
                     next(gens[wi])
@@ -285,7 +306,7 @@ def one_case(w, h, K, seed, land_late):
 
 def main():
     seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-    cases = [(20, 14, 3), (33, 28, 3), (40, 56, 3), (17, 70, 2), (64, 33, 1), (9, 100, 3), (50, 64, 4), (37, 32, 3), (5, 40, 3)]
+    cases = [(20, 14, 3), (33, 28, 3), (40, 56, 3), (17, 70, 2), (64, 33, 1), (9, 100, 3), (50, 64, 4), (37, 32, 3), (5, 40, 3), (3, 64, 3), (2, 33, 2), (130, 20, 3), (1, 96, 3)]
     bad = 0
     for (w, h, K) in cases:
         for seed in range(seeds):
