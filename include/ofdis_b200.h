@@ -196,9 +196,12 @@ int ofdis_set_direction(ofdis_ctx* ctx, int dir);
  *   red-black SOR (same system, omega and sweep count): NOT bit-identical to the reference --
  *   the flow differs by a few hundredths of a pixel (bench.py reports the delta) -- and never covered by the parity
  *   claim.  All other options are launch geometry (tuning / test hook), results are bit-identical under every setting:
- *   "sor_lane"        1 (default) | 0: refinement levels of few 32-row bands (<= 16 warps of bands x sweeps, within the
- *                     shared memory of an SM: up to 128 rows at 3 sweeps) run the SOR as a pixel wavefront whose warps
- *                     synchronise through shared-memory flags (sor_lane_kernel.cuh); 0 = the block wavefront everywhere
+ *   "sor_lane"        2 (default) | 1 | 0: refinement levels of few 32-row bands (bands x sweeps <= 12 warps within the
+ *                     shared memory of an SM; more sweeps than fit run in several launches) run the SOR as a wavefront of
+ *                     two-pixel blocks whose warps synchronise through shared-memory flags instead of a CTA barrier
+ *                     (sor_lane_kernel.cuh): 1 always, 0 never (the block wavefront of sor_wave_kernel everywhere),
+ *                     2 for launches of up to 16 frames -- it is ~20 % faster per launch but holds one CTA per SM at
+ *                     56-row levels, which costs throughput when several streams of large batches overlap
  *   "sor_rows_per_thread" 1 (default for flow) | 2 (default for stereo) | 4: rows of the 4-column tile one SOR thread updates per super-step
  *                     (a level needs W/4 + h/rows super-steps; sor_wave_kernel.cuh)
  *   "sor_single_max"  32 | 64 | 128 (default): refinement levels of up to this many SOR lanes (= rows / rows per

@@ -32,7 +32,12 @@ struct ofdis_ctx {
   // SOR band plan (sor_band_plan): levels of up to sor_single_max rows run in one CTA, taller ones in a
   // cluster of up to sor_max_cluster CTAs (8 = portable limit; 16 where the device grants it)
   int sor_single_max = 128, sor_max_cluster = 8, sor_dev_cluster = 8, sor_rt = 1;  // defaults set in ofdis_create
-  int sor_lane = 1;  // levels of few 32-row bands: pixel wavefront (sor_lane_kernel) instead of the block wavefront
+  // levels of few 32-row bands: pixel wavefront (sor_lane_kernel) instead of the block wavefront.  0 never, 1 always,
+  // 2 (default) for launches of up to SOR_LANE_AUTO_FRAMES frames: the kernel is ~20 % faster per launch but needs
+  // 200 KB of shared memory per CTA at 56-row levels (one CTA per SM), which costs 6 % of throughput when ten
+  // streams of 64 frames overlap (bench.py `value`)
+  int sor_lane = 2;
+  int last_vr_lane = 0;  // layout of the last refinement (ofdis_debug_get)
   int nlev = 0;                    // sc_f - sc_l + 1
   std::vector<LevelGeom> lev;      // index: level - sc_l
   std::vector<size_t> img_off;     // [lev][4] offsets (floats) inside one packed frame
@@ -62,6 +67,7 @@ struct ofdis_ctx {
 };
 
 namespace {
+constexpr int SOR_LANE_AUTO_FRAMES = 16;
 
 // NVTX range per stage and level ("patch L3", "densify L3", "varref L3", "pyramid", "upsample"): free
 // when no profiler is attached, names the stages in Nsight Systems / ncu --nvtx timelines.
@@ -654,7 +660,8 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
     return fail(ctx, OFDIS_ERR_UNSUPPORTED, "varref_refine: level too tall for the largest SOR cluster");
   pl.rec_stride = (size_t)pl.nb * pl.ndiag * pl.hpad * pl.lpitch;
   pl.lane = 0;
-  if (ctx->sor_lane && !pl.fast && sor_lane_fits(L->h, 1)) {  // lane-skewed layout, bands of 32 rows
+  const int nlaunch = (f1 - f0) * ctx->dirs;  // frames per launch
+  if ((ctx->sor_lane == 1 || (ctx->sor_lane == 2 && nlaunch <= SOR_LANE_AUTO_FRAMES)) && !pl.fast && sor_lane_fits(L->h, 1)) {  // lane-skewed layout, bands of 32 rows
     pl.lane = 1;
     pl.nb = (L->h + 31) / 32;
     pl.ndiag = lane_ndiag(L->w);
@@ -670,6 +677,7 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "varref kernels launch", cudaGetLastError());
   ctx->launches += n;
   ctx->last_vr_level = level;
+  ctx->last_vr_lane = pl.lane;
   ctx->last_vr_fcur = vp.n_inner & 1;
   ctx->last_vr_f0 = f0;
   ctx->last_vr_fstep = fwd_only ? 1 : D;  // workspace slots per user frame
@@ -701,7 +709,7 @@ int ofdis_set_option(ofdis_ctx* ctx, const char* name, int value) {
       return fail(ctx, OFDIS_ERR_UNSUPPORTED, "sor_max_cluster: the finest level needs the larger cluster");
     ctx->sor_max_cluster = value;
   } else if (!strcmp(name, "sor_lane")) {
-    if (value != 0 && value != 1) return fail(ctx, OFDIS_ERR_ARG, "sor_lane: 0 or 1");
+    if (value < 0 || value > 2) return fail(ctx, OFDIS_ERR_ARG, "sor_lane: 0, 1 or 2");
     ctx->sor_lane = value;
   } else if (!strcmp(name, "sor_fast")) {
     if (value != 0 && value != 1) return fail(ctx, OFDIS_ERR_ARG, "sor_fast: 0 or 1");
@@ -859,7 +867,7 @@ long ofdis_debug_get(ofdis_ctx* ctx, const char* name, int frame, float* dst, si
         for (int e = 0; e < per_f; ++e) dst[o * per_f + e] = is_rec ? raw[o * 8 + e] : raw[(size_t)e * plane + o];
       return (long)(plane * per_f);
     }
-    if (ctx->sor_lane && sor_lane_fits(L->h, 1)) {  // lane-skewed layout (VarRefPlanes, lane mode)
+    if (ctx->last_vr_lane) {  // lane-skewed layout (VarRefPlanes, lane mode)
       VarRefPlanes lp{};
       lp.nb = (L->h + 31) / 32;
       lp.ndiag = lane_ndiag(L->w);
