@@ -609,7 +609,26 @@ def main():
                 issue = {"warp_instructions_per_step": wi, "sms": sms, "sm_mhz": clocks["sm_mhz"],
                          "issue_slot_utilisation": wi / (ms_res * 1e-3 * sms * 4 * clocks["sm_mhz"] * 1e6),
                          "ipc_per_sm": wi / (ms_res * 1e-3 * sms * clocks["sm_mhz"] * 1e6)}
+        # the other exact SOR kernel (ofdis_set_option "sor_lane" 1: flag-synchronised warps, no CTA barrier) on the same
+        # batch, one stream: the engine picks it by itself for launches of up to 16 frames (batch_sweep below)
+        lane_alt = None
+        try:
+            cl = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, B, device=local, stream=stream.cuda_stream)
+            cl.set_option("sor_lane", 1)
+            cl.upload_packed(0, B, host_in.data_ptr())
+            cl.run(B)
+            pl_ = cl.profile_kernels(B, steps=max(3, min(args.steps, 10)))
+            cl.close()
+            lane_alt = {"kernel": "sor_lane_kernel (same sweeps; warps of 32 rows x two-pixel blocks, shuffles + flag-synchronised "
+                                  "shared-memory rings instead of a CTA barrier per super-step)",
+                        "kernel_ms_per_step": pl_["sor"]["ms_per_step"], "achieved": alg / (pl_["sor"]["ms_per_step"] * 1e-3) / 1e9,
+                        "frac": alg / (pl_["sor"]["ms_per_step"] * 1e-3) / 1e9 / peak,
+                        "note": "faster per launch, but 200 KB of shared memory per CTA at the 56-row level: with ten streams "
+                                "overlapping it costs 6 % of `value` (profiles/), so batches above 16 frames keep sor_wave_kernel"}
+        except Exception as e:
+            lane_alt = {"error": str(e)}
         roof = {"bound": "hbm", "kernel": "sor_wave_kernel (lexicographic SOR wavefront, all sweeps fused, one CTA per frame at this level size)", "achieved": ach,
+                "sor_lane_kernel": lane_alt,
                 "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_note": "ncu dram bytes per SOR launch with caches flushed before every replay (1.04x the "
                 "algorithmic bytes); 0.32e6 with --cache-control none, i.e. behind assemble_kernel in the level loop "
                 "(profiles/roofline_traffic.json)", "issue": issue, "peak_source": how,
@@ -643,8 +662,19 @@ def main():
                 e2e_b()
             ms2 = timed(e2e_b, 10)
             sweep[str(b)] = {"ms_per_step": ms, "value": b * H_ORG * W_ORG / (ms * 1e-3) / 1e6,
-                             "e2e_ms_per_step": ms2, "e2e_value": b * H_ORG * W_ORG / (ms2 * 1e-3) / 1e6}
+                             "e2e_ms_per_step": ms2, "e2e_value": b * H_ORG * W_ORG / (ms2 * 1e-3) / 1e6,
+                             "sor_kernel": "sor_lane_kernel (engine default for launches of up to 16 frames)",
+                             }
             c2.close()
+            c4 = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, b, device=local,
+                             stream=stream.cuda_stream)
+            c4.set_option("sor_lane", 0)  # A/B: the block wavefront (round 1/2 kernel) at the same batch
+            c4.upload_packed(0, b, host_in.data_ptr())
+            c4.set_graph_mode(True)
+            for _ in range(3):
+                c4.run(b)
+            sweep[str(b)]["sor_wave_kernel_ms_per_step"] = timed(lambda: c4.run(b), 10)
+            c4.close()
             if not args.no_extras:  # the same latency with the opt-in red-black refinement (see fast_mode)
                 c3 = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, b, device=local,
                                  stream=stream.cuda_stream)
