@@ -200,8 +200,9 @@ int ofdis_set_direction(ofdis_ctx* ctx, int dir);
  *                     shared memory of an SM; more sweeps than fit run in several launches) run the SOR as a wavefront of
  *                     two-pixel blocks whose warps synchronise through shared-memory flags instead of a CTA barrier
  *                     (sor_lane_kernel.cuh): 1 always, 0 never (the block wavefront of sor_wave_kernel everywhere),
- *                     2 for launches of up to 16 frames -- it is ~20 % faster per launch but holds one CTA per SM at
- *                     56-row levels, which costs throughput when several streams of large batches overlap
+ *                     2 for launches of up to 16 frames on levels of up to 64 rows -- there it is 10-20 % faster per
+ *                     launch; it holds one CTA per SM at 56-row levels, which costs throughput when several streams of
+ *                     large batches overlap, and every further band of rows adds start-up skew
  *   "sor_rows_per_thread" 1 (default for flow) | 2 (default for stereo) | 4: rows of the 4-column tile one SOR thread updates per super-step
  *                     (a level needs W/4 + h/rows super-steps; sor_wave_kernel.cuh)
  *   "sor_single_max"  32 | 64 | 128 (default): refinement levels of up to this many SOR lanes (= rows / rows per

@@ -33,7 +33,8 @@ struct ofdis_ctx {
   // cluster of up to sor_max_cluster CTAs (8 = portable limit; 16 where the device grants it)
   int sor_single_max = 128, sor_max_cluster = 8, sor_dev_cluster = 8, sor_rt = 1;  // defaults set in ofdis_create
   // levels of few 32-row bands: pixel wavefront (sor_lane_kernel) instead of the block wavefront.  0 never, 1 always,
-  // 2 (default) for launches of up to SOR_LANE_AUTO_FRAMES frames: the kernel is ~20 % faster per launch but needs
+  // 2 (default) for launches of up to SOR_LANE_AUTO_FRAMES frames on levels of one or two bands (sor_lane_preferred):
+  // there the kernel is 10-20 % faster per launch, but it needs
   // 200 KB of shared memory per CTA at 56-row levels (one CTA per SM), which costs 6 % of throughput when ten
   // streams of 64 frames overlap (bench.py `value`)
   int sor_lane = 2;
@@ -661,7 +662,8 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   pl.rec_stride = (size_t)pl.nb * pl.ndiag * pl.hpad * pl.lpitch;
   pl.lane = 0;
   const int nlaunch = (f1 - f0) * ctx->dirs;  // frames per launch
-  if ((ctx->sor_lane == 1 || (ctx->sor_lane == 2 && nlaunch <= SOR_LANE_AUTO_FRAMES)) && !pl.fast && sor_lane_fits(L->h, 1)) {  // lane-skewed layout, bands of 32 rows
+  if ((ctx->sor_lane == 1 || (ctx->sor_lane == 2 && nlaunch <= SOR_LANE_AUTO_FRAMES && sor_lane_preferred(L->h, ctx->prm.tv_solverit))) &&
+      !pl.fast && sor_lane_fits(L->h, 1)) {  // lane-skewed layout, bands of 32 rows
     pl.lane = 1;
     pl.nb = (L->h + 31) / 32;
     pl.ndiag = lane_ndiag(L->w);

@@ -196,6 +196,7 @@ int launch_varref(const LevelGeom& g, const VarRefPlanes& pl, const VarRefParams
 bool rb_smem_limit_exceeded(int nop, int K);
 // can sor_lane_kernel (pixel wavefront, one CTA per frame) take a level of h rows with K sweeps?
 bool sor_lane_fits(int h, int K);
+bool sor_lane_preferred(int h, int K);  // ... and is it the faster of the two exact kernels there?
 // largest thread-block cluster the SOR kernel can be launched with on the current device (8 or 16)
 int sor_max_cluster_size();
 

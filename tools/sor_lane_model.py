@@ -245,12 +245,12 @@ class Model:
                 if s % 2 == 0:
                     yield from ensure(t + 1)  # this step and the next
                 top = np.vstack((res[:1], res[:31]))
+                wait(D - 2)
+                yield
+                rec1, nxt1, bot1, th1 = load_operands(t + 1)
                 grp = []
                 issue(t + D, grp)
                 commit(grp)
-                wait(D - 1)
-                yield
-                rec1, nxt1, bot1, th1 = load_operands(t + 1)
                 act = row_ok & (I >= 0) & (I < W2)
                 self.reads_checked += int(act.sum()) + int((act & (2 * I + 1 < w)).sum())
                 if has_above:
