@@ -15,6 +15,8 @@
 // -fmad=false so nothing is contracted (bit-exactness).
 #include "ofdis_internal.cuh"
 
+#include <type_traits>
+
 namespace ofdis {
 
 namespace {
@@ -141,7 +143,9 @@ constexpr int TX = 32, TY = 8;
 // R rows per thread (tile 32 x 8R): the halo work of the two staging phases -- (TH+4)x36 flow
 // values and (TH+2)x34 smoothness weights per 32 x TH pixels -- shrinks from 1.69x / 1.33x (R=1)
 // to 1.27x / 1.13x (R=4).  All indices inside a frame are 32-bit.
-template <int C, int NOP, int R>
+// MODE: 0 = records for sor_wave_kernel (band_f4 lane rows), 1 = fast mode (natural layout), 2 = sor_lane_kernel
+// (lane-skewed layout); a template parameter so that the layout arithmetic of the other modes costs nothing.
+template <int C, int NOP, int R, int MODE>
 __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp,
                                                              int f0, int first) {
   constexpr int TH = TY * R;
@@ -156,15 +160,15 @@ __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPl
   // block holds field f of its 4 pixels, du is chunk nq, dv chunk nq+1.  Fast mode (red-black SOR):
   // natural layout, 8 floats per pixel, (du,dv) in the current ping-pong planes.
   // Lane mode (sor_lane_kernel): lane-skewed layout, the record is two float4 (lane_rec_f4), (du,dv) one float2.
-  const bool fast = pl.fast != 0, lane = pl.lane != 0;
+  constexpr bool fast = (MODE == 1), lane = (MODE == 2);
   float* const rec = fast ? pl.frec + (size_t)fr * pl.frec_stride : reinterpret_cast<float*>(pl.rec + (size_t)fr * pl.rec_stride);
   float* const dudv = fast ? pl.fdu + (size_t)fr * pl.fdu_stride + (size_t)pl.fcur * 2 * pl.plane : rec;
   const int fs = fast ? 1 : 4;                       // floats between consecutive record fields of a pixel
   const int dv_off = lane ? 1 : (fast ? (int)pl.plane : 4);  // from du to dv
-  auto rec_idx = [&pl, fast, lane, pitch](int x, int y) {
+  auto rec_idx = [&pl, pitch](int x, int y) {
     return lane ? (int)lane_rec_f4(pl, x, y, 0) * 4 : (fast ? (y * pitch + x) * 8 : (int)band_f4(pl, x >> 2, y, 0) * 4 + (x & 3));
   };
-  auto du_idx = [&pl, fast, lane, pitch](int x, int y) {
+  auto du_idx = [&pl, pitch](int x, int y) {
     return lane ? (int)lane_dudv_f(pl, x, y) : (fast ? y * pitch + x : (int)band_f4(pl, x >> 2, y, pl.nq) * 4 + (x & 3));
   };
 
@@ -560,9 +564,15 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl_in, const 
   for (int it = 0; it < vp.n_inner; ++it) {
     {
       ProfScope scope(prof, KC_VR_ASSEMBLE);
-      if (rows_per_thread == 4) assemble_kernel<C, NOP, 4><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
-      else if (rows_per_thread == 2) assemble_kernel<C, NOP, 2><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
-      else assemble_kernel<C, NOP, 1><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
+      auto launch_asm = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        if (rows_per_thread == 4) assemble_kernel<C, NOP, 4, MODE><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
+        else if (rows_per_thread == 2) assemble_kernel<C, NOP, 2, MODE><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
+        else assemble_kernel<C, NOP, 1, MODE><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
+      };
+      if (pl.fast) launch_asm(std::integral_constant<int, 1>{});
+      else if (pl.lane) launch_asm(std::integral_constant<int, 2>{});
+      else launch_asm(std::integral_constant<int, 0>{});
     }
     ++launches;
     if (pl.fast) {  // opt-in red-black solver: all K sweeps in one launch, (du,dv) ping-pong
