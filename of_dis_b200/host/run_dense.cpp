@@ -361,38 +361,42 @@ struct CliParams {
   bool usefbcon, usetvref;
 };
 
+// The four operating points (README.md:44-64 of the reference; run_dense.cpp:236-262): patch size, overlap, how many
+// levels below the automatically selected coarsest one the pyramid descends, Gauss-Newton iterations (max = min),
+// variational refinement on/off.  Index 0 is unused.
+struct OperatingPoint { int patchsz; float poverl; int levels_down, iters; bool usetvref; };
+const OperatingPoint kOperatingPoints[5] = {
+    {0, 0.f, 0, 0, false}, {8, 0.3f, 2, 16, false}, {8, 0.4f, 2, 12, true}, {12, 0.75f, 4, 16, true}, {12, 0.75f, 5, 128, true}};
+
 void parse_cli_params(int nnum, char** num, int width_org, CliParams& P) {
+  // defaults shared by all operating points
+  P.mindprate = 0.05f; P.mindrrate = 0.95f; P.minimgerr = 0.0f;
+  P.usefbcon = false; P.patnorm = 1; P.costfct = 0;
+  P.tv_alpha = 10.0f; P.tv_gamma = 10.0f; P.tv_delta = 5.0f;
+  P.tv_innerit = 1; P.tv_solverit = 3; P.tv_sor = 1.6f;
+  P.verbosity = 2;
   if (nnum <= 1) {
-    P.mindprate = 0.05; P.mindrrate = 0.95; P.minimgerr = 0.0;
-    P.usefbcon = 0; P.patnorm = 1; P.costfct = 0;
-    P.tv_alpha = 10.0; P.tv_gamma = 10.0; P.tv_delta = 5.0;
-    P.tv_innerit = 1; P.tv_solverit = 3; P.tv_sor = 1.6;
-    P.verbosity = 2;
-    const int fratio = 5;
-    int sel_oppoint = 2;
-    if (nnum == 1) sel_oppoint = atoi(num[0]);
-    switch (sel_oppoint) {
-      case 1: P.patchsz = 8; P.poverl = 0.3; P.lv_f = AutoFirstScaleSelect(width_org, fratio, P.patchsz);
-        P.lv_l = std::max(P.lv_f - 2, 0); P.maxiter = 16; P.miniter = 16; P.usetvref = 0; break;
-      case 3: P.patchsz = 12; P.poverl = 0.75; P.lv_f = AutoFirstScaleSelect(width_org, fratio, P.patchsz);
-        P.lv_l = std::max(P.lv_f - 4, 0); P.maxiter = 16; P.miniter = 16; P.usetvref = 1; break;
-      case 4: P.patchsz = 12; P.poverl = 0.75; P.lv_f = AutoFirstScaleSelect(width_org, fratio, P.patchsz);
-        P.lv_l = std::max(P.lv_f - 5, 0); P.maxiter = 128; P.miniter = 128; P.usetvref = 1; break;
-      case 2:
-      default: P.patchsz = 8; P.poverl = 0.4; P.lv_f = AutoFirstScaleSelect(width_org, fratio, P.patchsz);
-        P.lv_l = std::max(P.lv_f - 2, 0); P.maxiter = 12; P.miniter = 12; P.usetvref = 1; break;
-    }
-  } else {
-    int acnt = 0;
-    P.lv_f = atoi(num[acnt++]); P.lv_l = atoi(num[acnt++]);
-    P.maxiter = atoi(num[acnt++]); P.miniter = atoi(num[acnt++]);
-    P.mindprate = atof(num[acnt++]); P.mindrrate = atof(num[acnt++]); P.minimgerr = atof(num[acnt++]);
-    P.patchsz = atoi(num[acnt++]); P.poverl = atof(num[acnt++]);
-    P.usefbcon = atoi(num[acnt++]); P.patnorm = atoi(num[acnt++]); P.costfct = atoi(num[acnt++]);
-    P.usetvref = atoi(num[acnt++]);
-    P.tv_alpha = atof(num[acnt++]); P.tv_gamma = atof(num[acnt++]); P.tv_delta = atof(num[acnt++]);
-    P.tv_innerit = atoi(num[acnt++]); P.tv_solverit = atoi(num[acnt++]); P.tv_sor = atof(num[acnt++]);
-    P.verbosity = atoi(num[acnt++]);
+    int op = nnum == 1 ? atoi(num[0]) : 2;
+    if (op < 1 || op > 4) op = 2;  // anything else selects operating point 2, like the reference's default branch
+    const OperatingPoint& o = kOperatingPoints[op];
+    P.patchsz = o.patchsz;
+    P.poverl = o.poverl;
+    P.lv_f = AutoFirstScaleSelect(width_org, 5, o.patchsz);
+    P.lv_l = std::max(P.lv_f - o.levels_down, 0);
+    P.maxiter = P.miniter = o.iters;
+    P.usetvref = o.usetvref;
+    return;
+  }
+  // the 20 explicit numbers, in the order of the reference's README (README.md:66-88)
+  const struct { char kind; void* dst; } fields[20] = {
+      {'i', &P.lv_f}, {'i', &P.lv_l}, {'i', &P.maxiter}, {'i', &P.miniter}, {'f', &P.mindprate}, {'f', &P.mindrrate},
+      {'f', &P.minimgerr}, {'i', &P.patchsz}, {'f', &P.poverl}, {'b', &P.usefbcon}, {'i', &P.patnorm}, {'i', &P.costfct},
+      {'b', &P.usetvref}, {'f', &P.tv_alpha}, {'f', &P.tv_gamma}, {'f', &P.tv_delta}, {'i', &P.tv_innerit},
+      {'i', &P.tv_solverit}, {'f', &P.tv_sor}, {'i', &P.verbosity}};
+  for (int k = 0; k < 20; ++k) {
+    if (fields[k].kind == 'i') *static_cast<int*>(fields[k].dst) = atoi(num[k]);
+    else if (fields[k].kind == 'f') *static_cast<float*>(fields[k].dst) = (float)atof(num[k]);
+    else *static_cast<bool*>(fields[k].dst) = atoi(num[k]) != 0;
   }
 }
 
