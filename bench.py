@@ -663,8 +663,7 @@ def main():
             ms2 = timed(e2e_b, 10)
             sweep[str(b)] = {"ms_per_step": ms, "value": b * H_ORG * W_ORG / (ms * 1e-3) / 1e6,
                              "e2e_ms_per_step": ms2, "e2e_value": b * H_ORG * W_ORG / (ms2 * 1e-3) / 1e6,
-                             "sor_kernel": "sor_lane_kernel (engine default for launches of up to 16 frames)",
-                             }
+                             "sor_kernel": "sor_lane_kernel (engine default for launches of up to 16 frames)"}
             c2.close()
             c4 = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, b, device=local,
                              stream=stream.cuda_stream)
