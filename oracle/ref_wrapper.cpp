@@ -187,11 +187,14 @@ double ofdis_ref_run_many(const float*** ptrs, int npairs, int nrep, int threads
   std::vector<std::thread> pool;
   for (int t = 0; t < threads; ++t)
     pool.emplace_back([&]() {
+      // OFClass refines its output array in place, so two passes over the same pair (nrep > 1) must not share it:
+      // every run writes a per-thread scratch; the result is copied out afterwards (all passes produce the same bits)
+      std::vector<float> scratch(outflow_stride);
       for (long i = next.fetch_add(1); i < total; i = next.fetch_add(1)) {
         const int q = (int)(i % npairs);
         const float*** pp = ptrs + (size_t)q * 6;
-        ofdis_ref_run(pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], imgpadding, outflow + (size_t)q * outflow_stride, nullptr,
-                      width, height, p);
+        ofdis_ref_run(pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], imgpadding, scratch.data(), nullptr, width, height, p);
+        if (i < npairs) std::memcpy(outflow + (size_t)q * outflow_stride, scratch.data(), sizeof(float) * outflow_stride);
       }
     });
   for (auto& th : pool) th.join();
