@@ -203,6 +203,9 @@ int ofdis_set_direction(ofdis_ctx* ctx, int dir);
  *                     2 for launches of up to 16 frames on levels of up to 64 rows -- there it is 10-20 % faster per
  *                     launch; it holds one CTA per SM at 56-row levels, which costs throughput when several streams of
  *                     large batches overlap, and every further band of rows adds start-up skew
+ *   "pdl"             2 (default) | 1 | 0: programmatic dependent launch of the level loop's kernels (every kernel starts
+ *                     with griddepcontrol.wait, so the next kernel's launch overlaps the tail of the current one):
+ *                     1 always, 0 never, 2 for launches of up to 16 frames (2-5 % of the step there; larger batches lose)
  *   "sor_rows_per_thread" 1 (default for flow) | 2 (default for stereo) | 4: rows of the 4-column tile one SOR thread updates per super-step
  *                     (a level needs W/4 + h/rows super-steps; sor_wave_kernel.cuh)
  *   "sor_single_max"  32 | 64 | 128 (default): refinement levels of up to this many SOR lanes (= rows / rows per

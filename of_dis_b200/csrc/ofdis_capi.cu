@@ -39,6 +39,11 @@ struct ofdis_ctx {
   // streams of 64 frames overlap (bench.py `value`)
   int sor_lane = 2;
   int last_vr_lane = 0;  // layout of the last refinement (ofdis_debug_get)
+  // programmatic dependent launch of the level loop's kernels (pdl_wait, ofdis_internal.cuh): 0 never, 1 always,
+  // 2 (default) for launches of up to SOR_LANE_AUTO_FRAMES frames: one stream, graph replay, tools/pdl_ab.py:
+  // 1 pair 0.349 -> 0.342 ms, 8 pairs 0.373 -> 0.356 ms, 64 pairs 0.558 -> 0.598 ms (waiting CTAs of the next kernel
+  // take SM slots from the tail of the current one)
+  int pdl = 2;
   int nlev = 0;                    // sc_f - sc_l + 1
   std::vector<LevelGeom> lev;      // index: level - sc_l
   std::vector<size_t> img_off;     // [lev][4] offsets (floats) inside one packed frame
@@ -610,6 +615,7 @@ int ofdis_patgrid_optimize(ofdis_ctx* ctx, int level, int f0, int f1, int init_f
   NvtxRange nvtx("patch", level);
   const int q0 = ctx->sel_dir >= 0 ? f0 * ctx->dirs + ctx->sel_dir : f0 * ctx->dirs;
   const int q1 = ctx->sel_dir >= 0 ? q0 + 1 : f1 * ctx->dirs;
+  L->pdl = (ctx->pdl == 1 || (ctx->pdl == 2 && q1 - q0 <= SOR_LANE_AUTO_FRAMES)) ? 1 : 0;
   const int n = launch_patch_optimize(*L, ctx->pp, q0, q1, init_from_coarser != 0, ctx->stream, ctx->prof);
   if (n < 0) return fail(ctx, OFDIS_ERR_CUDA, "patch_optimize_kernel launch", cudaGetLastError());
   ctx->launches += n;
@@ -662,6 +668,7 @@ static int varref_impl(ofdis_ctx* ctx, int level, int f0, int f1, int n_inner_ov
   pl.rec_stride = (size_t)pl.nb * pl.ndiag * pl.hpad * pl.lpitch;
   pl.lane = 0;
   const int nlaunch = (f1 - f0) * ctx->dirs;  // frames per launch
+  L->pdl = (ctx->pdl == 1 || (ctx->pdl == 2 && nlaunch <= SOR_LANE_AUTO_FRAMES)) ? 1 : 0;
   if ((ctx->sor_lane == 1 || (ctx->sor_lane == 2 && nlaunch <= SOR_LANE_AUTO_FRAMES && sor_lane_preferred(L->h, ctx->prm.tv_solverit))) &&
       !pl.fast && sor_lane_fits(L->h, 1)) {  // lane-skewed layout, bands of 32 rows
     pl.lane = 1;
@@ -713,6 +720,9 @@ int ofdis_set_option(ofdis_ctx* ctx, const char* name, int value) {
   } else if (!strcmp(name, "sor_lane")) {
     if (value < 0 || value > 2) return fail(ctx, OFDIS_ERR_ARG, "sor_lane: 0, 1 or 2");
     ctx->sor_lane = value;
+  } else if (!strcmp(name, "pdl")) {
+    if (value < 0 || value > 2) return fail(ctx, OFDIS_ERR_ARG, "pdl: 0, 1 or 2");
+    ctx->pdl = value;
   } else if (!strcmp(name, "sor_fast")) {
     if (value != 0 && value != 1) return fail(ctx, OFDIS_ERR_ARG, "sor_fast: 0 or 1");
     if (!ctx->d_planes) return fail(ctx, OFDIS_ERR_ARG, "sor_fast: context created with usetvref=0");

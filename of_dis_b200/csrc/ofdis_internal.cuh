@@ -14,6 +14,7 @@ struct LevelGeom {
   int w, h, pad, tmp_w, tmp_h;
   int noc, nop, P, novals, steps, nopw, noph, np, offw, offh;
   int level, camlr;
+  int pdl;                 // launch the level loop's kernels with programmatic dependent launch (see pdl_wait)
   int pitch;               // row pitch (floats) of the planar refinement planes, multiple of 4
   float lb, ubw, ubh, outlierthresh;
   // device pointers (frame 0); frame f adds f * stride
@@ -199,6 +200,33 @@ bool sor_lane_fits(int h, int K);
 bool sor_lane_preferred(int h, int K);  // ... and is it the faster of the two exact kernels there?
 // largest thread-block cluster the SOR kernel can be launched with on the current device (8 or 16)
 int sor_max_cluster_size();
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------
+// Every kernel starts with pdl_wait(): a kernel launched with the programmatic-stream-serialization attribute may be
+// scheduled while its predecessor in the stream still runs (its launch latency and CTA start-up overlap the
+// predecessor's tail); griddepcontrol.wait then blocks until the predecessor has completed and its memory
+// operations are visible, griddepcontrol.launch_dependents lets this kernel's own successor be scheduled as soon
+// as all of this kernel's CTAs have started.  Without the attribute both instructions do nothing.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory");
+}
+// launch with or without the attribute (g.pdl, set per context: ofdis_set_option "pdl")
+template <typename... KP, typename... A>
+static inline cudaError_t launch_k(bool pdl, void (*kern)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KP>(args)...);
+}
+#endif
 
 // ---- exact-arithmetic helpers -------------------------------------------------
 // std::min/std::max semantics of the reference (operand order matters for +-0/NaN)

@@ -44,6 +44,7 @@ __device__ __forceinline__ float fold8(float acc, float tailv, bool has_strided,
 template <int NOP>
 __global__ void __launch_bounds__(256) patch_optimize_kernel(LevelGeom g, PatchParams pp, int f0,
                                                               int init_from_coarser) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ float smem[];
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int l8 = tid & 7;
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(256) patch_optimize_kernel(LevelGeom g, PatchP
 template <int NOP>
 __global__ void __launch_bounds__(256) patch_p8c1_kernel(LevelGeom g, PatchParams pp, int f0,
                                                           int init_from_coarser) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int tid = threadIdx.x;
   const int l8 = tid & 7;
   const int frame = f0 + blockIdx.y;
@@ -553,6 +555,7 @@ template <int NOP, int C, bool TMA>
 __global__ void __launch_bounds__(256, C == 1 ? 2 : 1) patch_p12_kernel(LevelGeom g, PatchParams pp, int f0,
                                                                         int init_from_coarser,
                                                                         const __grid_constant__ CUtensorMap tmap) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   using Cfg = PwCfg<C>;
   constexpr int P = Cfg::P, M = Cfg::M, W = Cfg::W, PC = Cfg::PC, NK = Cfg::NK;
   constexpr int WH = PwWin<NOP, C, TMA>::WH;    // window rows
@@ -932,6 +935,7 @@ __device__ __forceinline__ void densify_merge_complement(const LevelGeom& g, int
 // performs the same float additions in the same order, without atomics.
 template <int NOP>
 __global__ void __launch_bounds__(256) densify_kernel(LevelGeom g, int f0) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int xi = blockIdx.x * blockDim.x + threadIdx.x;
   const int yi = blockIdx.y * blockDim.y + threadIdx.y;
   const int frame = frame_of(g, f0, blockIdx.z);
@@ -989,6 +993,7 @@ __global__ void __launch_bounds__(256) densify_kernel(LevelGeom g, int f0) {
 // Swapped copy of the image pair into the backward frame of every couple: its template is I1,
 // its target I0 (oflow.cpp:193-197).  Gradients are derived afterwards by sobel_kernel.
 __global__ void __launch_bounds__(256) swap_images_kernel(LevelGeom g, int f0) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const size_t n = (size_t)g.tmp_w * g.tmp_h * g.noc;
   const int fwd = f0 + 2 * blockIdx.y, bwd = fwd + 1;
   const float* a = g.img[0] + (size_t)fwd * g.img_fs[0];
@@ -1006,6 +1011,7 @@ __global__ void __launch_bounds__(256) swap_images_kernel(LevelGeom g, int f0) {
 // (bounds the gather window of densify_merge_complement exactly).  One CTA per frame.
 template <int NOP>
 __global__ void __launch_bounds__(256) fb_prepare_kernel(LevelGeom g, int f0) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   __shared__ int s_max[256];
   const int frame = f0 + blockIdx.x;
   const float* pp = g.pat_p + (size_t)frame * g.np * NOP;
@@ -1045,8 +1051,8 @@ int launch_patch_optimize(const LevelGeom& g, const PatchParams& pp, int f0, int
   ProfScope scope(prof, KC_PATCH);
   if (g.P == 8 && g.noc == 1) {  // register-resident specialisation (operating points 1 and 2)
     const dim3 grid8((g.np + 31) / 32, f1 - f0);
-    if (g.nop == 2) patch_p8c1_kernel<2><<<grid8, 256, 0, st>>>(g, pp, f0, init_from_coarser ? 1 : 0);
-    else patch_p8c1_kernel<1><<<grid8, 256, 0, st>>>(g, pp, f0, init_from_coarser ? 1 : 0);
+    if (g.nop == 2) launch_k(g.pdl && !prof, patch_p8c1_kernel<2>, dim3(grid8), dim3(256), 0, st, g, pp, f0, init_from_coarser ? 1 : 0);
+    else launch_k(g.pdl && !prof, patch_p8c1_kernel<1>, dim3(grid8), dim3(256), 0, st, g, pp, f0, init_from_coarser ? 1 : 0);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
   if (g.P == 12 && g.pad >= 12 && (g.noc == 1 || g.noc == 3)) {  // window-staged specialisation (operating points 3 and 4)
@@ -1138,8 +1144,8 @@ int launch_swap_images(const LevelGeom& g, int f0, int f1, cudaStream_t st) {  /
 int launch_densify(const LevelGeom& g, int f0, int f1, cudaStream_t st, Profiler* prof) {
   ProfScope scope(prof, KC_DENSIFY);
   const dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8, f1 - f0);
-  if (g.nop == 2) densify_kernel<2><<<grid, block, 0, st>>>(g, f0);
-  else densify_kernel<1><<<grid, block, 0, st>>>(g, f0);
+  if (g.nop == 2) launch_k(g.pdl && !prof, densify_kernel<2>, grid, block, 0, st, g, f0);
+  else launch_k(g.pdl && !prof, densify_kernel<1>, grid, block, 0, st, g, f0);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -16,6 +16,7 @@ namespace {
 // The divisibility padding (replicate, floor(pad/2) left/top) and the per-level border padding
 // (replicate, g.pad) are folded into the index clamps.  One thread per padded destination pixel.
 __global__ void __launch_bounds__(256) pyr_from_u8_kernel(LevelGeom g, int f0, PyrSourceU8 s) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int xp = blockIdx.x * blockDim.x + threadIdx.x, yp = blockIdx.y * blockDim.y + threadIdx.y;
   if (xp >= g.tmp_w || yp >= g.tmp_h) return;
   const int fr = blockIdx.z >> 1, k = blockIdx.z & 1;  // k: 0 = I0, 1 = I1
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) pyr_from_u8_kernel(LevelGeom g, int f0, P
 
 // Border padding of un-padded float images of level g.level ([frame][2][h][w][C], I0 then I1).
 __global__ void __launch_bounds__(256) pyr_from_level_kernel(LevelGeom g, int f0, const float* stage) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int xp = blockIdx.x * blockDim.x + threadIdx.x, yp = blockIdx.y * blockDim.y + threadIdx.y;
   if (xp >= g.tmp_w || yp >= g.tmp_h) return;
   const int fr = blockIdx.z >> 1, k = blockIdx.z & 1;
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(256) pyr_from_level_kernel(LevelGeom g, int f0
 // ((a+b)+(c+d))*0.25 with a,b the even row; reads the interior of the padded level gs, writes
 // level gd = gs+1 including its replicate border.
 __global__ void __launch_bounds__(256) pyr_down_kernel(LevelGeom gs, LevelGeom gd, int f0) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int xp = blockIdx.x * blockDim.x + threadIdx.x, yp = blockIdx.y * blockDim.y + threadIdx.y;
   if (xp >= gd.tmp_w || yp >= gd.tmp_h) return;
   const int fr = blockIdx.z >> 1, k = blockIdx.z & 1;
@@ -71,6 +74,7 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(LevelGeom gs, LevelGeom g
 // (row difference first, then the [1 2 1]/8 column sum, and vice versa for dy); for images that
 // come from 8-bit input every intermediate is exact, so this equals OpenCV bit for bit.
 __global__ void __launch_bounds__(256) sobel_kernel(LevelGeom g, int f0) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int xp = blockIdx.x * blockDim.x + threadIdx.x, yp = blockIdx.y * blockDim.y + threadIdx.y;
   const int frame = frame_of(g, f0, blockIdx.z);
   if (xp >= g.tmp_w || yp >= g.tmp_h) return;
@@ -107,6 +111,7 @@ __global__ void __launch_bounds__(256) sobel_kernel(LevelGeom g, int f0) {
 template <int NOP>
 __global__ void __launch_bounds__(256) flow_upsample_kernel(LevelGeom g, int f0, float* out, int w_org, int h_org,
                                                             int crop_x, int crop_y) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y * blockDim.y + threadIdx.y;
   if (X >= w_org || Y >= h_org) return;
   const int fr = blockIdx.z;

@@ -26,6 +26,7 @@ __host__ __device__ inline size_t rb_smem_bytes(int nop, int K) {
 
 template <int NOP>
 __global__ void __launch_bounds__(256) sor_redblack_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   extern __shared__ float rb_smem[];
   constexpr int NR = (NOP == 2) ? 7 : 4;  // staged record planes
   const int K = vp.n_solver, H = 2 * K, S = RB_TILE + 2 * H, SS = S * S;

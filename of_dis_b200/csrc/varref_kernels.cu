@@ -73,6 +73,7 @@ __device__ __forceinline__ float conv_v5(const float* q, int pitch, int h, int j
 // the first loop of get_derivatives (opticalflow_aux.c:80-84).
 template <int C, int NOP>
 __global__ void __launch_bounds__(256) warp_kernel(LevelGeom g, VarRefPlanes pl, int f0) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
   const int fr = blockIdx.z, frame = frame_of(g, f0, fr);
   if (i >= g.w || j >= g.h) return;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(256) warp_kernel(LevelGeom g, VarRefPlanes pl,
 // get_derivatives, first-order planes (opticalflow_aux.c:86-87,91-92)
 template <int C>
 __global__ void __launch_bounds__(256) deriv1_kernel(LevelGeom g, VarRefPlanes pl) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= g.w || j >= g.h) return;
   const Coef5 c5 = coef5();
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(256) deriv1_kernel(LevelGeom g, VarRefPlanes p
 // get_derivatives, second-order planes (opticalflow_aux.c:88-90)
 template <int C>
 __global__ void __launch_bounds__(256) deriv2_kernel(LevelGeom g, VarRefPlanes pl) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= g.w || j >= g.h) return;
   const Coef5 c5 = coef5();
@@ -148,6 +151,7 @@ constexpr int TX = 32, TY = 8;
 template <int C, int NOP, int R, int MODE>
 __global__ void __launch_bounds__(TX * TY) assemble_kernel(LevelGeom g, VarRefPlanes pl, VarRefParams vp,
                                                              int f0, int first) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   constexpr int TH = TY * R;
   __shared__ float2 s_uv[TH + 4][TX + 4];
   __shared__ float s_s[TH + 2][TX + 2];
@@ -452,6 +456,7 @@ __device__ __forceinline__ void sts128(unsigned addr, const float4& v) {
 // from one-thread-per-row SOR lanes costs 32 cache lines per load instruction.
 template <int NOP>
 __global__ void __launch_bounds__(256) flow_update_kernel(LevelGeom g, VarRefPlanes pl, int f0) {
+  pdl_wait();  // programmatic dependent launch: nothing of the previous kernel is touched before this
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
   const int fr = blockIdx.z, frame = frame_of(g, f0, fr);
   if (i >= g.w || j >= g.h) return;
@@ -501,15 +506,22 @@ static cudaError_t launch_sor_t(const LevelGeom& g, const VarRefPlanes& pl, cons
   cfg.blockDim = dim3((unsigned)(kl * HPAD + 32));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (CL) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)pl.nb;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)pl.nb;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (g.pdl) {  // see pdl_wait (ofdis_internal.cuh)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, g, pl, vp, kl);
 }
 
@@ -539,6 +551,7 @@ template <int C, int NOP>
 static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl_in, const VarRefParams& vp, int f0, int f1,
                            cudaStream_t st, Profiler* prof) {
   VarRefPlanes pl = pl_in;  // fast mode toggles the (du,dv) ping-pong buffer
+  const bool pdl = g.pdl != 0 && prof == nullptr;  // the profiler's events between launches would serialise them anyway
   pl.fcur = 0;
   int launches = 0;
   const int nf = f1 - f0;
@@ -551,9 +564,9 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl_in, const 
   const dim3 grid_a(grid.x, (g.h + TY * rows_per_thread - 1) / (TY * rows_per_thread), nf);
   {
     ProfScope scope(prof, KC_VR_SETUP);
-    warp_kernel<C, NOP><<<grid, block, 0, st>>>(g, pl, f0);
-    deriv1_kernel<C><<<gridc, block, 0, st>>>(g, pl);
-    deriv2_kernel<C><<<gridc, block, 0, st>>>(g, pl);
+    launch_k(pdl, warp_kernel<C, NOP>, grid, block, 0, st, g, pl, f0);
+    launch_k(pdl, deriv1_kernel<C>, gridc, block, 0, st, g, pl);
+    launch_k(pdl, deriv2_kernel<C>, gridc, block, 0, st, g, pl);
   }
   launches += 3;
   // SOR: band plan of the level (pl.hpad rows per band, pl.nb bands == CTAs of a cluster) and as
@@ -566,9 +579,9 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl_in, const 
       ProfScope scope(prof, KC_VR_ASSEMBLE);
       auto launch_asm = [&](auto mode_tag) {
         constexpr int MODE = decltype(mode_tag)::value;
-        if (rows_per_thread == 4) assemble_kernel<C, NOP, 4, MODE><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
-        else if (rows_per_thread == 2) assemble_kernel<C, NOP, 2, MODE><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
-        else assemble_kernel<C, NOP, 1, MODE><<<grid_a, block, 0, st>>>(g, pl, vp, f0, it == 0 ? 1 : 0);
+        if (rows_per_thread == 4) launch_k(pdl, assemble_kernel<C, NOP, 4, MODE>, grid_a, block, 0, st, g, pl, vp, f0, it == 0 ? 1 : 0);
+        else if (rows_per_thread == 2) launch_k(pdl, assemble_kernel<C, NOP, 2, MODE>, grid_a, block, 0, st, g, pl, vp, f0, it == 0 ? 1 : 0);
+        else launch_k(pdl, assemble_kernel<C, NOP, 1, MODE>, grid_a, block, 0, st, g, pl, vp, f0, it == 0 ? 1 : 0);
       };
       if (pl.fast) launch_asm(std::integral_constant<int, 1>{});
       else if (pl.lane) launch_asm(std::integral_constant<int, 2>{});
@@ -587,7 +600,7 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl_in, const 
         smem_set[dev] = smem;
       }
       const dim3 grid_rb((g.w + RB_TILE - 1) / RB_TILE, (g.h + RB_TILE - 1) / RB_TILE, nf);
-      sor_redblack_kernel<NOP><<<grid_rb, 256, smem, st>>>(g, pl, vp);
+      launch_k(pdl, sor_redblack_kernel<NOP>, grid_rb, dim3(256), smem, st, g, pl, vp);
       pl.fcur ^= 1;
       ++launches;
       continue;
@@ -606,7 +619,7 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl_in, const 
           if (cudaFuncSetAttribute(sor_lane_kernel<NOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
           smem_set[dev] = smem;
         }
-        sor_lane_kernel<NOP><<<nf, pl.nb * kk * 32, smem, st>>>(g, pl, vp, kk);
+        launch_k(pdl, sor_lane_kernel<NOP>, dim3(nf), dim3(pl.nb * kk * 32), smem, st, g, pl, vp, kk);
         ++launches;
       }
       continue;
@@ -619,7 +632,7 @@ static int launch_varref_t(const LevelGeom& g, const VarRefPlanes& pl_in, const 
   }
   if (vp.n_inner > 0) {
     ProfScope scope(prof, KC_VR_SETUP);
-    flow_update_kernel<NOP><<<grid, block, 0, st>>>(g, pl, f0);
+    launch_k(pdl, flow_update_kernel<NOP>, grid, block, 0, st, g, pl, f0);
     ++launches;
   }
   return cudaGetLastError() == cudaSuccess ? launches : -1;

@@ -323,6 +323,32 @@ def test_sor_tile_heights_vs_oracle(name, rt, api, oracle_port):
     ctx.close()
 
 
+@pytest.mark.parametrize("pdl", [0, 1])
+@pytest.mark.parametrize("name", ["cfg2_1024x436_gray_op2", "rgb_op3_l1cost_small", "stereo_op4_small"])
+def test_programmatic_dependent_launch_vs_oracle(name, pdl, api, oracle_port):
+    """ofdis_set_option("pdl"): every kernel starts with griddepcontrol.wait; with the launch attribute the next kernel
+    is scheduled while the current one drains.  Eager and graph replay, four frames per launch, several replays:
+    the reference's bits every time."""
+    h, w, ch, mk, amp, stereo = CASES[name]
+    prm = mk()
+    pyrs = []
+    for s in range(4):
+        i0, i1, _ = synth.synthetic_pair(h, w, ch, seed=21 + s, amp=amp, stereo=stereo)
+        pyrs.append(preprocess.PairPyramids(i0, i1, prm.sc_f, prm.p_samp_s))
+    ctx = api.Context(prm, pyrs[0].width, pyrs[0].height, pyrs[0].imgpadding, 4)
+    ctx.set_option("pdl", pdl)
+    for f, p in enumerate(pyrs):
+        ctx.upload_pyramids(f, p)
+    exp = [oracle_port.port_run(p, prm) for p in pyrs]
+    for graph in (False, True):
+        ctx.set_graph_mode(graph)
+        for rep in range(3):
+            ctx.run(4)
+            for f in range(4):
+                assert_bits(ctx.get_flow(f, prm.sc_l), exp[f], "pdl=%d graph=%s replay %d frame %d" % (pdl, graph, rep, f))
+    ctx.close()
+
+
 LANE_CASES = ["cfg2_1024x436_gray_op2", "cfg1_640x480_gray_op2", "rgb_op3_l1cost_small", "stereo_op4_small",
               "gray_p6_nopatnorm_sor5", "gray_sor2_rows70", "stereo_sor1_rows100"]
 
