@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "of_dis_b200", "lib", "libofdis_b200.so")
-KEY = ["UBLKCP", "UTMALDG", "SYNCS", "STAS", "UCGABAR", "MUFU.RCP", "MUFU.RSQ", "FCHK", "CALL", "BAR.SYNC", "LDS", "STS",
+KEY = ["UBLKCP", "UTMALDG", "SYNCS", "STAS", "UCGABAR", "LDGSTS", "LDGDEPBAR", "DEPBAR", "CREDUX", "ACQBULK", "MUFU.RCP", "MUFU.RSQ", "FCHK", "CALL", "BAR.SYNC", "LDS", "STS",
        "LDG", "STG", "SHFL", "VOTE", "FFMA", "FMUL", "FADD", "FSEL", "MEMBAR", "FENCE", "CCTL"]
 
 
