@@ -6,6 +6,8 @@
 // rounding modifier and -fmad=false is given to nvcc and to ptxas (the scalar forms are never contracted then):
 //   FMUL2 R12, R12.F32x2.HI_LO, UR7.F32 ; FFMA2 R12, R4.F32x2.HI_LO, UR6.F32, R12.F32x2.HI_LO
 // A fused product is rounded once, the reference's SSE build rounds twice: not usable for the bit-exact path as is.
+// The all-FMA spelling -- product = fma.rn.f32x2(a, b, -0), sum = fma.rn.f32x2(p, 1, q), each exactly one rounding -- is
+// canonicalised back to mul/add and contracted the same way.
 // (The broadcast operand form `UR7.F32` shows that a scalar times a pair needs no packing instruction.)
 #include <cuda_runtime.h>
 __device__ __forceinline__ unsigned long long pk(float a, float b){unsigned long long r; asm("mov.b64 %0, {%1,%2};":"=l"(r):"f"(a),"f"(b)); return r;}
