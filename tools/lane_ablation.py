@@ -18,7 +18,7 @@ def build():
     procs = []
     for v in ONLY or (list(VARIANTS) + ["t"]):
         out = os.path.join(EXP, "libofdis_lane%s.so" % v)
-        defs = ["-DOFDIS_SOR_TIMING"] if v == "t" else (["-DOFDIS_EXP_UNROLL=%s" % v[1:]] if str(v).startswith("u") else ["-DOFDIS_EXP_LANE=%s" % v])
+        defs = ["-DOFDIS_SOR_TIMING"] if v == "t" else (["-DOFDIS_EXP_UNROLL=%s" % v[1:]] if str(v).startswith("u") else (["-DOFDIS_EXP_SLP=%s" % v[1:]] if str(v).startswith("p") else ["-DOFDIS_EXP_LANE=%s" % v]))
         cmd = [B._nvcc()] + B.NVCC_FLAGS + defs + [os.path.join(B.CSRC, s) for s in B.SOURCES] + ["-ldl", "-o", out]
         procs.append((v, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for v, p in procs:
@@ -62,7 +62,7 @@ def child(timeline):
     print(json.dumps(out))
 
 
-ONLY = [a for a in sys.argv[1:] if not a.startswith("--")]  # e.g. 0 5 u1 u2 u4 (uN: product with the step loop unrolled N times)
+ONLY = [a for a in sys.argv[1:] if not a.startswith("--")]  # e.g. 0 5 u1 u2 u4 p2 p8 (uN: product with the step loop unrolled N times; pN: progress published every N steps)
 
 if __name__ == "__main__":
     if "--build" in sys.argv:
