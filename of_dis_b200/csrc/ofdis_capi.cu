@@ -628,6 +628,7 @@ int ofdis_patgrid_aggregate(ofdis_ctx* ctx, int level, int f0, int f1) {
   if (!L || f0 < 0 || f1 > ctx->max_frames || f0 >= f1) return fail(ctx, OFDIS_ERR_ARG, "patgrid_aggregate: bad argument");
   CK(cudaSetDevice(ctx->device));
   NvtxRange nvtx("densify", level);
+  L->pdl = (ctx->pdl == 1 || (ctx->pdl == 2 && (f1 - f0) * ctx->dirs <= SOR_LANE_AUTO_FRAMES)) ? 1 : 0;
   int n;
   if (ctx->dirs == 2) {
     // both grids' patch positions first; the backward flow is not densified on the last level (oflow.cpp:269-270)
